@@ -82,6 +82,7 @@ SYMBOLS = {
                                           C.POINTER(C.c_int32)]),
     "enumgpu_partial_to_result": (None, [C.POINTER(Partial), C.POINTER(Result)]),
     "enumgpu_merge_partial": (None, [C.POINTER(Partial), C.POINTER(Partial)]),
+    "enumgpu_shard_begin": (C.c_uint64, [C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32]),
     "enumgpu_fp64_peak_tflops": (C.c_double, [C.c_int32]),
 }
 

@@ -1,0 +1,145 @@
+"""Host-side mirror of the reference's solver interface for the enumeration path.
+
+``Canonical`` keeps the reference's getter names (reference:
+src/ProblemTypes/Canonical.h:10-49, Canonical.cpp:126-154) and constructor
+validation (Canonical.cpp:27-46); ``EnumerationSolver`` has the call shape of
+the reference's ``Solver`` (src/SimplexSolover.h:285-288): construct from a
+Canonical, ``solve()`` returns the first ``GetOriginalVariablesCount()``
+components of the optimal x (SimplexSolover.h:435-439) and raises
+``RuntimeError`` when the LP has no feasible basis (cf. SimplexSolover.h:371).
+
+All numerical work happens in libenumgpu (CUDA, sm_100a) behind the C ABI of
+include/enumgpu.h; this module only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._lib import EnumGpuError, last_error, lib
+
+
+class Canonical:
+    """min/max c'x, Ax = b, x >= 0 with a designated basis (reference Canonical)."""
+
+    def __init__(self, A, b, c, basisIndices: Sequence[int], minimize: bool = True):
+        A = np.asarray(A, dtype=np.float64)
+        b = np.asarray(b, dtype=np.float64).reshape(-1)
+        c = np.asarray(c, dtype=np.float64).reshape(-1)
+        if A.ndim != 2:
+            raise ValueError("A must be a matrix")
+        # same checks, same order, as Canonical.cpp:27-46
+        if A.shape[0] != b.size:
+            raise ValueError("dimensions of A and b do not match")
+        if A.shape[1] != c.size:
+            raise ValueError("dimensions of A and c do not match")
+        if len(basisIndices) != A.shape[0]:
+            raise ValueError("number of basis indices differs from the number of rows of A")
+        for idx in basisIndices:
+            if idx < 0 or idx >= A.shape[1]:
+                raise ValueError("basis index out of range")
+        self._A = np.asfortranarray(A)          # Eigen default storage: column-major
+        self._b = np.ascontiguousarray(b)
+        self._c = np.ascontiguousarray(c)
+        self._basis = [int(i) for i in basisIndices]
+        self._minimize = bool(minimize)
+        self._n_orig = int(c.size)              # Canonical.cpp:25
+
+    # -- reference getters (Canonical.cpp:126-154) -------------------------
+    def GetConstraintsMatrix(self): return self._A
+    def GetRightHandSide(self): return self._b
+    def GetObjectiveCoefficients(self): return self._c
+    def IsMaximization(self): return not self._minimize
+    def GetBasisIndices(self): return self._basis
+    def GetOriginalVariablesCount(self): return self._n_orig
+
+    def SetOriginalVariablesCount(self, count: int):
+        if count <= 0 or count > self._c.size:      # Canonical.cpp:156-163
+            raise ValueError("invalid number of original variables")
+        self._n_orig = int(count)
+
+    def Evaluate(self, solution) -> float:
+        x = np.asarray(solution, dtype=np.float64).reshape(-1)
+        if x.size != self._c.size:                  # Canonical.cpp:81-84
+            raise ValueError("solution size differs from the number of variables")
+        return float(self._c @ x)
+
+
+def _problem_struct(A, b, c, maximize):
+    m, n = A.shape
+    return _abi.Problem(m, n, A.strides[1] // 8 if n > 1 else m, int(bool(maximize)),
+                        A.ctypes.data, b.ctypes.data, c.ctypes.data)
+
+
+def _check(rc: int):
+    if rc == _abi.ERR_CUDA:
+        raise EnumGpuError(last_error())
+    if rc in (_abi.ERR_ARG, _abi.ERR_RANGE, _abi.ERR_NONFINITE):
+        raise ValueError(last_error())
+
+
+class EnumerationSolver:
+    """Solve a Canonical LP by enumerating all C(n, m) bases on the GPU(s).
+
+    >>> x = EnumerationSolver(canonical).solve()          # like Solver(problem).solve()
+    """
+
+    def __init__(self, problem: Canonical, devices: Optional[Sequence[int]] = None,
+                 algo: int = _abi.ALGO_AUTO, eps_feas: float = 1e-9, eps_piv: float = 1e-9):
+        A = problem.GetConstraintsMatrix()
+        m, n = A.shape
+        if m > n:
+            raise ValueError(f"m={m} > n={n}: no basis exists")
+        if m > _abi.MAX_M or n > _abi.MAX_N:
+            raise ValueError(f"(m,n)=({m},{n}) above the library limits ({_abi.MAX_M},{_abi.MAX_N})")
+        self._problem = problem                      # reference copies (SimplexSolover.h:12,285); arrays are not mutated here
+        self._devices = None if devices is None else [int(d) for d in devices]
+        self._algo = int(algo)
+        self._eps = (float(eps_feas), float(eps_piv))
+        self._res: Optional[_abi.Result] = None
+
+    # -- the reference call shape ------------------------------------------
+    def solve(self, rank_begin: int = 0, rank_end: int = 0) -> np.ndarray:
+        res = self.enumerate(rank_begin, rank_end)
+        if res.status == _abi.NO_FEASIBLE:
+            raise RuntimeError("the problem has no feasible basic solution")
+        p = self._problem
+        x = np.zeros(p.GetObjectiveCoefficients().size)
+        for i in range(res.m):
+            x[res.basis[i]] = res.x_B[i]
+        return x[: p.GetOriginalVariablesCount()].copy()
+
+    def enumerate(self, rank_begin: int = 0, rank_end: int = 0) -> _abi.Result:
+        """Run the enumeration and return the raw result struct (no exception on NO_FEASIBLE)."""
+        p = self._problem
+        A, b, c = p.GetConstraintsMatrix(), p.GetRightHandSide(), p.GetObjectiveCoefficients()
+        ps = _problem_struct(A, b, c, p.IsMaximization())
+        nd = 0 if self._devices is None else len(self._devices)
+        dev = (C.c_int32 * max(nd, 1))(*(self._devices or [0]))
+        o = _abi.Options(self._eps[0], self._eps[1], rank_begin, rank_end, nd, self._algo,
+                         C.cast(dev, C.POINTER(C.c_int32)) if nd else None, None)
+        res = _abi.Result()
+        rc = lib().enumgpu_solve(C.byref(ps), C.byref(o), C.byref(res))
+        _check(rc)
+        self._res = res
+        return res
+
+    # -- accessors the parity metric needs (not in the reference) -----------
+    def _need(self) -> _abi.Result:
+        if self._res is None:
+            raise RuntimeError("solve() has not been called")
+        return self._res
+
+    def optimalBasis(self): r = self._need(); return [int(r.basis[i]) for i in range(r.m)]
+    def basicValues(self): r = self._need(); return [float(r.x_B[i]) for i in range(r.m)]
+    def objective(self): return float(self._need().objective)
+    def bestRank(self): return int(self._need().best_rank)
+    def basesEvaluated(self): return int(self._need().n_bases)
+    def singularCount(self): return int(self._need().n_singular)
+    def infeasibleCount(self): return int(self._need().n_infeasible)
+    def feasibleCount(self): return int(self._need().n_feasible)
+    def kernelMilliseconds(self): return float(self._need().kernel_ms)
+    def launches(self): return int(self._need().n_launches)

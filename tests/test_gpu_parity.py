@@ -1,0 +1,229 @@
+"""GPU: libenumgpu (through the C ABI) against the CPU oracle, bit for bit."""
+import ctypes as C
+import json
+import os
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import simplexmethod_b200 as sm
+from simplexmethod_b200 import _abi, lpgen
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ALGOS = [_abi.ALGO_INDEPENDENT, _abi.ALGO_SHARED]
+
+
+def gpu_solve(A, b, c, mx, algo=_abi.ALGO_AUTO, devices=None, **rng):
+    can = sm.Canonical(A, b, c, list(range(A.shape[0])), minimize=not mx)
+    s = sm.EnumerationSolver(can, devices=devices, algo=algo)
+    return s.enumerate(**rng)
+
+
+def assert_same(g, o, m, bitexact=True):
+    assert g.status == o.status
+    assert (g.n_bases, g.n_singular, g.n_infeasible, g.n_feasible) == \
+           (o.n_bases, o.n_singular, o.n_infeasible, o.n_feasible)
+    assert g.best_rank == o.best_rank
+    if o.status == 0:
+        assert list(g.basis)[:m] == list(o.basis)[:m]
+        if bitexact:
+            assert g.objective == o.objective and g.key == o.key          # same bits (== also accepts +-0)
+            assert list(g.x_B)[:m] == list(o.x_B)[:m]
+        else:
+            assert g.objective == pytest.approx(o.objective, rel=1e-9)
+
+
+with open(os.path.join(HERE, "golden", "tiny_lps.json")) as f:
+    GOLD = json.load(f)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_tiny_goldens(gpu_lib, oracle, name, algo):
+    g = GOLD[name]
+    A = np.array(g["A"]); m, n = A.shape
+    res = gpu_solve(A, g["b"], g["c"], g["maximize"], algo)
+    assert (res.n_singular, res.n_infeasible, res.n_feasible) == (g["n_singular"], g["n_infeasible"], g["n_feasible"])
+    assert res.best_rank == g["best_rank"] and list(res.basis)[:m] == g["best_basis"]
+    assert res.objective == pytest.approx(float(Fraction(g["best_z"])), rel=1e-12, abs=1e-12)
+    o, _ = oracle.solve(A, g["b"], g["c"], g["maximize"])
+    assert_same(res, o, m)
+
+
+def test_reference_call_shape_config1(gpu_lib):
+    """input_symmetric.txt -> ToCanonical -> EnumerationSolver(problem).solve() == (5,0,0), z = 35."""
+    A, b, c, mx = lpgen.lab_symmetric_canonical()
+    can = sm.Canonical(A, b, c, [3, 4], minimize=False)
+    can.SetOriginalVariablesCount(3)
+    s = sm.EnumerationSolver(can)
+    x = s.solve()
+    assert x.tolist() == [5.0, 0.0, 0.0] and s.objective() == 35.0 and s.optimalBasis() == [0, 3]
+    assert (s.singularCount(), s.infeasibleCount(), s.feasibleCount(), s.basesEvaluated()) == (0, 3, 7, 10)
+    assert can.Evaluate(np.r_[x, 0, 0]) == 35.0
+    assert s.launches() >= 2
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("m,n,seed", [(1, 1, 1), (1, 7, 2), (2, 2, 3), (3, 9, 4), (4, 4, 5), (4, 11, 6), (5, 12, 7),
+                                      (6, 13, 8), (7, 15, 9), (9, 14, 10), (11, 15, 11), (13, 15, 12), (16, 17, 13)])
+def test_small_shapes_full_range(gpu_lib, oracle, m, n, seed, algo):
+    A, b, c, mx = lpgen.dense_lp(m, n, seed)
+    for maximize in (False, True):
+        res = gpu_solve(A, b, c, maximize, algo)
+        o, _ = oracle.solve(A, b, c, maximize, n_threads=4)
+        assert_same(res, o, m)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_config2_dense_8_24(gpu_lib, oracle, seed, algo):
+    A, b, c, mx = lpgen.dense_lp(8, 24, seed)
+    res = gpu_solve(A, b, c, mx, algo)
+    o, _ = oracle.solve(A, b, c, mx, n_threads=os.cpu_count())
+    assert res.n_bases == 735471
+    assert_same(res, o, 8)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_config3_dense_10_30(gpu_lib, oracle, algo):
+    A, b, c, mx = lpgen.dense_lp(10, 30, 1)
+    res = gpu_solve(A, b, c, mx, algo)
+    o, _ = oracle.solve(A, b, c, mx, n_threads=os.cpu_count())
+    assert res.n_bases == 30045015
+    assert_same(res, o, 10)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_config5_degenerate_tie_break(gpu_lib, oracle, algo):
+    """Beale-style m=10, n=30: counters and best rank identical; lowest rank wins exact ties."""
+    A, b, c, mx = lpgen.degenerate_lp()
+    res = gpu_solve(A, b, c, mx, algo)
+    o, _ = oracle.solve(A, b, c, mx, n_threads=os.cpu_count())
+    assert o.n_singular > 10**6 and o.n_feasible > 1000
+    assert_same(res, o, 10)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_rank_ranges_and_merge(gpu_lib, oracle, algo):
+    """Arbitrary half-open ranges, empty range, and merge of disjoint ranges == full run."""
+    A, b, c, mx = lpgen.dense_lp(6, 16, 21)
+    total = 8008
+    full = gpu_solve(A, b, c, mx, algo)
+    cuts = [0, 1, 17, 1000, 1001, 4097, 8007, total]
+    acc = None
+    for a, e in zip(cuts[:-1], cuts[1:]):
+        part = gpu_solve(A, b, c, mx, algo, rank_begin=a, rank_end=e)
+        o, _ = oracle.solve(A, b, c, mx, rank_begin=a, rank_end=e)
+        assert_same(part, o, 6)
+        acc = part if acc is None else acc
+        if part is not acc:
+            if (part.key, part.best_rank) < (acc.key, acc.best_rank) and part.status == 0:
+                part.n_feasible += acc.n_feasible; part.n_infeasible += acc.n_infeasible
+                acc = part
+            else:
+                acc.n_feasible += part.n_feasible; acc.n_infeasible += part.n_infeasible
+    assert (acc.best_rank, acc.n_feasible, acc.n_infeasible) == (full.best_rank, full.n_feasible, full.n_infeasible)
+    empty = gpu_solve(A, b, c, mx, algo, rank_begin=5, rank_end=5)
+    assert empty.status == _abi.NO_FEASIBLE and empty.n_bases == 0
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_infeasible_lp_reports_no_feasible(gpu_lib, algo):
+    A = np.asfortranarray(np.array([[1.0, 1.0, 1.0], [1.0, 2.0, 3.0]]))
+    can = sm.Canonical(A, [-1.0, -1.0], [1.0, 1.0, 1.0], [0, 1])
+    s = sm.EnumerationSolver(can, algo=algo)
+    with pytest.raises(RuntimeError, match="no feasible"):
+        s.solve()
+    assert s.feasibleCount() == 0 and s.basesEvaluated() == 3
+
+
+def test_lda_padding_and_device_entry(gpu_lib, oracle):
+    """lda > m through the host entry; device-resident entry with torch-owned buffers and stream."""
+    import torch
+    A, b, c, mx = lpgen.dense_lp(7, 18, 33)
+    o, _ = oracle.solve(A, b, c, mx, n_threads=4)
+    pad = np.zeros((10, 18), order="F"); pad[:7] = A
+    ps = _abi.Problem(7, 18, 10, 0, pad.ctypes.data, b.ctypes.data, c.ctypes.data)
+    res = _abi.Result()
+    assert gpu_lib.enumgpu_solve(C.byref(ps), None, C.byref(res)) == 0
+    assert_same(res, o, 7)
+
+    dA = torch.from_numpy(np.ascontiguousarray(A.T)).cuda()      # row-major (n, m) == column-major (m, n)
+    db, dc = torch.from_numpy(b).cuda(), torch.from_numpy(c).cuda()
+    pd = _abi.Problem(7, 18, 7, 0, dA.data_ptr(), db.data_ptr(), dc.data_ptr())
+    for scale in (float(np.abs(A).max()), -1.0):
+        opt = _abi.Options(-1, -1, 0, 0, 0, 0, None, torch.cuda.current_stream().cuda_stream)
+        res2 = _abi.Result()
+        assert gpu_lib.enumgpu_solve_device(C.byref(pd), scale, C.byref(opt), C.byref(res2)) == 0, sm.last_error()
+        assert_same(res2, o, 7)
+        assert res2.kernel_ms > 0
+
+
+def test_enqueue_device_async_partial(gpu_lib, oracle):
+    import torch
+    A, b, c, mx = lpgen.dense_lp(8, 20, 5)
+    o, _ = oracle.solve(A, b, c, mx, n_threads=4)
+    dA = torch.from_numpy(np.ascontiguousarray(A.T)).cuda()
+    db, dc = torch.from_numpy(b).cuda(), torch.from_numpy(c).cuda()
+    pd = _abi.Problem(8, 20, 8, 0, dA.data_ptr(), db.data_ptr(), dc.data_ptr())
+    half = 125970 // 2
+    parts = []
+    for a, e in ((0, half), (half, 125970)):
+        buf = torch.zeros(256, dtype=torch.uint8, device="cuda")
+        opt = _abi.Options(-1, -1, a, e, 0, 0, None, torch.cuda.current_stream().cuda_stream)
+        nl = C.c_int32()
+        assert gpu_lib.enumgpu_enqueue_device(C.byref(pd), float(np.abs(A).max()), C.byref(opt), buf.data_ptr(), C.byref(nl)) == 0
+        assert nl.value >= 2
+        parts.append(buf)
+    torch.cuda.synchronize()
+    recs = [_abi.Partial.from_buffer_copy(p.cpu().numpy().tobytes()) for p in parts]
+    gpu_lib.enumgpu_merge_partial(C.byref(recs[0]), C.byref(recs[1]))
+    res = _abi.Result()
+    gpu_lib.enumgpu_partial_to_result(C.byref(recs[0]), C.byref(res))
+    assert_same(res, o, 8)
+
+
+def test_headline_12_40_prefix_and_windows(gpu_lib, oracle):
+    """m=12, n=40: a 2e6-rank prefix and pseudo-random windows, GPU == oracle bit for bit."""
+    A, b, c, mx = lpgen.dense_lp(12, 40, 1)
+    total = 5586853480
+    rng = np.random.default_rng(12)
+    starts = [0] + [int(v) for v in rng.integers(0, total - 400000, 4)] + [total - 300000]
+    for s0 in starts:
+        e0 = min(total, s0 + (2000000 if s0 == 0 else 300000))
+        res = gpu_solve(A, b, c, mx, rank_begin=s0, rank_end=e0)
+        o, _ = oracle.solve(A, b, c, mx, n_threads=os.cpu_count(), rank_begin=s0, rank_end=e0)
+        assert_same(res, o, 12)
+
+
+def test_headline_12_40_full_vs_golden(gpu_lib):
+    """Full C(40,12) enumeration against the committed CPU-oracle golden (one-off 8-core run)."""
+    path = os.path.join(HERE, "golden", "dense_12_40_seed1.json")
+    if not os.path.exists(path):
+        pytest.skip("golden for the full 12x40 run not generated")
+    g = json.load(open(path))
+    A, b, c, mx = lpgen.dense_lp(12, 40, 1)
+    res = gpu_solve(A, b, c, mx)
+    assert res.status == g["status"] and res.n_bases == g["n_bases"] == 5586853480
+    assert (res.n_singular, res.n_infeasible, res.n_feasible) == (g["n_singular"], g["n_infeasible"], g["n_feasible"])
+    assert res.best_rank == g["best_rank"] and list(res.basis)[:12] == g["basis"]
+    assert float(res.objective).hex() == g["objective"]
+    assert [float(v).hex() for v in list(res.x_B)[:12]] == g["x_B"]
+    # size-independent property: the optimum satisfies B x_B = b and is what HiGHS finds
+    B = A[:, g["basis"]]
+    assert np.allclose(B @ np.array(list(res.x_B)[:12]), b, rtol=0, atol=1e-9)
+    from scipy.optimize import linprog
+    h = linprog(c, A_eq=A, b_eq=b, bounds=(0, None), method="highs")
+    assert res.objective == pytest.approx(h.fun, rel=1e-9)
+
+
+def test_multi_device_in_process(gpu_lib, oracle):
+    """n_devices > 1 inside one process: contiguous shards, host merge; same answer."""
+    nd = gpu_lib.enumgpu_device_count()
+    A, b, c, mx = lpgen.dense_lp(8, 24, 2)
+    o, _ = oracle.solve(A, b, c, mx, n_threads=os.cpu_count())
+    for devs in ([0], [0, 0, 0], list(range(nd))):
+        res = gpu_solve(A, b, c, mx, devices=devs)
+        assert_same(res, o, 8)
