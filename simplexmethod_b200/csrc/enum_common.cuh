@@ -82,9 +82,9 @@ __device__ __forceinline__ double fnma(double a, double b, double c) { return __
 template <int kThreads>
 __device__ __forceinline__ void block_reduce(double& key, uint64_t& rank,
                                              uint32_t& ns, uint32_t& ni, uint32_t& nf,
-                                             BlockPartial* out_slot)
+                                             BlockPartial* out_slot, int n_warps = kThreads / 32)
 {
-    constexpr int kWarps = kThreads / 32;
+    constexpr int kWarps = kThreads / 32;   // capacity; n_warps <= kWarps are live
     __shared__ double   s_key[kWarps];
     __shared__ uint64_t s_rank[kWarps];
     __shared__ uint32_t s_cnt[kWarps][3];
@@ -104,7 +104,7 @@ __device__ __forceinline__ void block_reduce(double& key, uint64_t& rank,
     if (threadIdx.x == 0) {
         double bk = s_key[0]; uint64_t br = s_rank[0];
         uint64_t cs = s_cnt[0][0], ci = s_cnt[0][1], cf = s_cnt[0][2];
-        for (int w = 1; w < kWarps; ++w) {
+        for (int w = 1; w < n_warps; ++w) {
             if (better(s_key[w], s_rank[w], bk, br)) { bk = s_key[w]; br = s_rank[w]; }
             cs += s_cnt[w][0]; ci += s_cnt[w][1]; cf += s_cnt[w][2];
         }
