@@ -1,0 +1,56 @@
+"""Join an ncu report's SASS page with nvdisasm line info: executed warp-instructions,
+stall samples and shared-memory wavefronts per CUDA source line, plus the opcode mix.
+usage: ncu_lines.py report.ncu-rep mangled_kernel_prefix [top_n]   (run where ncu/nvdisasm exist)"""
+import csv, io, os, re, subprocess, sys, tempfile
+
+rep, kern = sys.argv[1], sys.argv[2]
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+so = os.path.join(root, "simplexmethod_b200", "libenumgpu.so")
+tmp = tempfile.mkdtemp()
+subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL)
+cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.split("\n")
+start = [i for i, l in enumerate(sass) if l.startswith(".text." + kern)][0]
+end = next((i for i, l in enumerate(sass) if i > start and l.strip().startswith(".section")), len(sass))
+cur, addr2line = None, {}
+for l in sass[start:end]:
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+    if m:
+        cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
+    m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
+    if m:
+        addr2line[int(m.group(1), 16)] = cur
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
+h = rows[hi]
+ix, isamp, ia, iw, iwi = (h.index(k) for k in ("Instructions Executed", "# Samples", "Address", "L1 Wavefronts Shared", "L1 Wavefronts Shared Ideal"))
+base = int(rows[hi + 1][ia], 16)
+agg, opagg, tot, tsamp = {}, {}, 0, 0
+for r in rows[hi + 1:]:
+    if len(r) <= ix or not r[ix].isdigit():
+        continue
+    off = int(r[ia], 16) - base
+    c, s = int(r[ix]), int(r[isamp]) if r[isamp].isdigit() else 0
+    w = int(r[iw]) if r[iw].isdigit() else 0
+    wi = int(r[iwi]) if r[iwi].isdigit() else 0
+    tot += c; tsamp += s
+    a = agg.setdefault(addr2line.get(off), [0, 0, 0, 0]); a[0] += c; a[1] += s; a[2] += w; a[3] += wi
+    ins = r[1].split()
+    op = (ins[1] if ins[0].startswith("@") else ins[0]).split(".")[0]
+    o = opagg.setdefault(op, [0, 0]); o[0] += c; o[1] += s
+print(f"total executed warp-instructions {tot}, samples {tsamp}")
+srcs = {}
+for key, (c, s, w, wi) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    if key is None:
+        print(f"{100*c/tot:5.1f}% inst {100*s/tsamp:5.1f}% samp  (no line)"); continue
+    f, l = key
+    path = os.path.join(root, "simplexmethod_b200", "csrc", f)
+    if f not in srcs:
+        srcs[f] = open(path).read().split("\n") if os.path.exists(path) else None
+    text = srcs[f][l - 1].strip()[:88] if srcs[f] else ""
+    print(f"{100*c/tot:5.1f}% inst {100*s/tsamp:5.1f}% samp  wf {w}/{wi}  {f}:{l}: {text}")
+print()
+for op, (c, s) in sorted(opagg.items(), key=lambda kv: -kv[1][0])[:28]:
+    print(f"{op:10s} {100*c/tot:5.1f}% inst {100*s/tsamp:5.1f}% samp")
