@@ -194,8 +194,8 @@ def main():
     algo = {"auto": _abi.ALGO_AUTO, "independent": _abi.ALGO_INDEPENDENT, "shared": _abi.ALGO_SHARED}[args.algo]
 
     # this rank's shard (strong scaling: same LP, contiguous rank ranges)
-    lo = L.enumgpu_shard_begin(m, n, 0, total, rank, world)
-    hi = L.enumgpu_shard_begin(m, n, 0, total, rank + 1, world)
+    from simplexmethod_b200 import dist as edist
+    lo, hi = edist.shard_bounds(m, n, rank, world)
 
     # inputs resident in HBM
     dA = torch.from_numpy(np.ascontiguousarray(A.T)).to(dev)
@@ -214,19 +214,10 @@ def main():
         rc = L.enumgpu_enqueue_device(C.byref(pd), scale, C.byref(opt), part.data_ptr(), C.byref(nl))
         if rc != 0:
             raise RuntimeError(sm.last_error())
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, part)
-        else:
-            gathered.copy_(part)
+        edist.all_gather_records(part, gathered, world)
 
     def merged_result():
-        host = gathered.cpu().numpy().tobytes()
-        recs = [_abi.Partial.from_buffer_copy(host[i * 256:(i + 1) * 256]) for i in range(world)]
-        for r in recs[1:]:
-            L.enumgpu_merge_partial(C.byref(recs[0]), C.byref(r))
-        res = _abi.Result()
-        L.enumgpu_partial_to_result(C.byref(recs[0]), C.byref(res))
-        return res
+        return edist.merge_records(gathered.cpu().numpy().tobytes(), world)
 
     def barrier():
         if world > 1:
@@ -257,10 +248,7 @@ def main():
         if rc != 0:
             raise RuntimeError(sm.last_error())
         ev[i][1].record(stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, part)
-        else:
-            gathered.copy_(part)
+        edist.all_gather_records(part, gathered, world)
     barrier()
     wall = max_over_ranks(time.perf_counter() - t0)
     launches_per_step = nl.value + 2                 # + flush fill + gather/copy

@@ -1,0 +1,92 @@
+// host_tests.cpp — CPU-only checks of the host types, restating what the
+// reference's gtest suite pins for them (reference: tests/test_canonical.cpp:
+// 31-39,68-76; tests/test_symmetrical.cpp:27-97; tests/test_parser.cpp:4-81).
+// Exit code 0 = all passed.  Needs no GPU (no numerical method is called).
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+
+#include "EnumerationSolver.h"
+#include "ProblemTypes/Canonical.h"
+#include "ProblemTypes/Symmetrical.h"
+#include "SymmetricalParser.h"
+
+#define CHECK(cond) do { if (!(cond)) { std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); std::exit(1); } } while (0)
+template <class E, class F> static bool throws(F&& f) { try { f(); } catch (const E&) { return true; } catch (...) { return false; } return false; }
+
+static Eigen::MatrixXd mat(int r, int c, std::initializer_list<double> rowmajor)
+{
+    Eigen::MatrixXd m(r, c);
+    int k = 0;
+    for (double v : rowmajor) { m(k / c, k % c) = v; ++k; }
+    return m;
+}
+
+int main()
+{
+    // --- Canonical: fixture of tests/test_canonical.cpp:12-22
+    const Eigen::MatrixXd A = mat(2, 4, {1, 2, 1, 0, 3, 4, 0, 1});
+    Eigen::VectorXd b(2); b[0] = 5; b[1] = 6;
+    Eigen::VectorXd c(4); c[0] = 7; c[1] = 8; c[2] = 0; c[3] = 0;
+    Canonical can(A, b, c, {2, 3}, true);
+    CHECK(can.GetConstraintsMatrix().rows() == 2 && can.GetConstraintsMatrix().cols() == 4);
+    CHECK(can.GetRightHandSide().size() == 2 && can.GetObjectiveCoefficients().size() == 4);
+    CHECK(!can.IsMaximization());
+    CHECK(can.GetBasisIndices().size() == 2 && can.GetBasisIndices()[0] == 2);
+    CHECK(can.GetOriginalVariablesCount() == 4);
+    CHECK(can.GetConstraintsMatrix().data()[1] == 3.0);                 // column-major: A(1,0)
+    CHECK(throws<std::invalid_argument>([&] { Canonical bad(A, b, c, {2, 10}, true); }));
+    CHECK(throws<std::invalid_argument>([&] { Canonical bad(A, b, c, {2}, true); }));
+    CHECK(throws<std::invalid_argument>([&] { can.SetOriginalVariablesCount(0); }));
+    Eigen::VectorXd x(4); x[0] = 1; x[1] = 2; x[2] = 0; x[3] = 0;
+    CHECK(can.Evaluate(x) == 23.0);                                     // 7*1 + 8*2, cf. test_common.cpp:57-58
+    CHECK(throws<std::invalid_argument>([&] { can.Evaluate(b); }));
+    Canonical copy(can);                                               // value semantics
+    copy.SetOriginalVariablesCount(2);
+    CHECK(can.GetOriginalVariablesCount() == 4 && copy.GetOriginalVariablesCount() == 2);
+
+    // --- Symmetrical -> Canonical (tests/test_symmetrical.cpp:64-71, 83-84) and the dual (:47-52)
+    const Eigen::MatrixXd As = mat(2, 2, {1, 2, 3, 4});
+    Eigen::VectorXd bs(2); bs[0] = 5; bs[1] = 6;
+    Eigen::VectorXd cs(2); cs[0] = 7; cs[1] = 8;
+    Symmetrical smax(As, bs, cs, true);
+    auto cmax = smax.ToCanonical();
+    CHECK(cmax->GetConstraintsMatrix().cols() == 4 && cmax->IsMaximization());
+    CHECK(cmax->GetBasisIndices()[0] == 2 && cmax->GetBasisIndices()[1] == 3);
+    CHECK(cmax->GetOriginalVariablesCount() == 2);
+    CHECK(cmax->GetConstraintsMatrix()(0, 2) == 1.0 && cmax->GetConstraintsMatrix()(1, 2) == 0.0 && cmax->GetConstraintsMatrix()(1, 3) == 1.0);
+    Symmetrical smin(As, bs, cs, false);
+    auto cmin = smin.ToCanonical();
+    CHECK(cmin->GetConstraintsMatrix().cols() == 6 && !cmin->IsMaximization());
+    CHECK(cmin->GetConstraintsMatrix()(0, 2) == -1.0 && cmin->GetConstraintsMatrix()(0, 4) == 1.0);
+    CHECK(cmin->GetBasisIndices()[0] == 4 && cmin->GetObjectiveCoefficients()[4] == 0.0);
+    auto dual = smax.GetDual();
+    CHECK(!dual->IsMaximization() && dual->GetConstraintsMatrix()(0, 1) == 3.0);
+    CHECK(dual->GetRightHandSide()[1] == 8.0 && dual->GetObjectiveCoefficients()[0] == 5.0);
+    CHECK(throws<std::invalid_argument>([&] { Symmetrical bad(As, cs, c, true); }));
+
+    // --- parser (tests/test_parser.cpp)
+    SymmetricalParser parser;
+    auto p1 = parser.ParseFromString("\n  maximize\n\n objective:\n 3 5\n\n constraints:\n 1 2 10\n 3 4 20\n");
+    CHECK(p1 && p1->IsMaximization() && p1->GetConstraintsMatrix().rows() == 2 && p1->GetConstraintsMatrix().cols() == 2);
+    CHECK(p1->GetRightHandSide()[1] == 20.0 && p1->GetConstraintsMatrix()(1, 0) == 3.0);
+    auto p2 = parser.ParseFromString("minimize\nobjective:\n7 8\nsubject to:\n1 1 5\n2 3 12\n");
+    CHECK(p2 && !p2->IsMaximization());
+    auto p3 = parser.ParseFromString("# c\nmax\n# f\nobjective:\n1 2 3  # more\nconstraints:\n1 0 0 5 # a\r\n0 1 0 6\r\n0 0 1 7\r\n");
+    CHECK(p3 && p3->GetObjectiveCoefficients().size() == 3 && p3->GetConstraintsMatrix().rows() == 3);
+    auto p4 = parser.ParseFromString("maximize\n# nothing else\n");
+    CHECK(!p4 && !parser.GetLastError().empty());
+    CHECK(!parser.ParseFromString("1 2 3\n"));                             // data outside a section
+    CHECK(!parser.ParseFromString("max\nobjective:\n1 2\nconstraints:\n1 2 3 4\n"));   // width mismatch
+    CHECK(!parser.ParseFromFile("/nonexistent/file.txt"));
+
+    // --- EnumerationSolver: argument checks that need no device
+    CHECK(throws<std::invalid_argument>([&] {
+        Canonical tall(mat(3, 2, {1, 0, 0, 1, 1, 1}), Eigen::VectorXd(3), Eigen::VectorXd(2), {0, 1, 1}, true);
+        EnumerationSolver s(tall);
+    }));
+    EnumerationSolver s(can);
+    CHECK(throws<std::logic_error>([&] { s.objective(); }));
+    std::puts("host_tests: all passed");
+    return 0;
+}

@@ -68,6 +68,31 @@ class Canonical:
         return float(self._c @ x)
 
 
+    # -- per-basis numerics: on the GPU, through enumgpu_eval_basis ---------
+    def _eval_designated(self):
+        ps = _problem_struct(self._A, self._b, self._c, not self._minimize)
+        m = self._A.shape[0]
+        basis = (C.c_int32 * m)(*self._basis)
+        x = (C.c_double * m)()
+        z, cls = C.c_double(), C.c_int32()
+        _check(lib().enumgpu_eval_basis(C.byref(ps), None, basis, x, C.byref(z), C.byref(cls)))
+        return cls.value, list(x), z.value
+
+    def GetBasicSolution(self):
+        """x (length n) of the designated basis (reference Canonical.cpp:179-197); singular -> RuntimeError."""
+        cls, xB, _ = self._eval_designated()
+        if cls == 2:
+            raise RuntimeError("Singular basis matrix")
+        x = np.zeros(self._c.size)
+        for j, v in zip(self._basis, xB):
+            x[j] = v
+        return x
+
+    def IsFeasibleBasis(self) -> bool:
+        """All basic values >= -1e-9 (reference Canonical.cpp:165-177)."""
+        return self._eval_designated()[0] == 0
+
+
 def _problem_struct(A, b, c, maximize):
     m, n = A.shape
     return _abi.Problem(m, n, A.strides[1] // 8 if n > 1 else m, int(bool(maximize)),
