@@ -151,7 +151,7 @@ def main():
     A, b, c, mx = lpgen.dense_lp(m, n, args.seed)
     workload = f"dense canonical LP m={m} n={n} seed={args.seed}: full enumeration of C({n},{m})={total} bases"
     config = {"workload": workload, "m": m, "n": n, "seed": args.seed, "bases_per_step": total,
-              "sharding": f"{world} contiguous rank ranges" if world > 1 else "single GPU",
+              "sharding": f"{world} shards of interleaved contiguous rank windows" if world > 1 else "single GPU",
               "l2": "inputs are 4.3 KB staged once per CTA in shared memory; compute-bound, L2 state "
                     "irrelevant; a 256 MB buffer is rewritten between timed steps anyway"}
 
@@ -193,9 +193,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     algo = {"auto": _abi.ALGO_AUTO, "independent": _abi.ALGO_INDEPENDENT, "shared": _abi.ALGO_SHARED}[args.algo]
 
-    # this rank's shard (strong scaling: same LP, contiguous rank ranges)
+    # this rank's shard (strong scaling: same LP): the interleaved rank windows
+    # rank, rank+world, ... of the whole space (enumgpu_options.shard_index/count)
     from simplexmethod_b200 import dist as edist
-    lo, hi = edist.shard_bounds(m, n, rank, world)
+    lo, hi = 0, total
 
     # inputs resident in HBM
     dA = torch.from_numpy(np.ascontiguousarray(A.T)).to(dev)
@@ -203,7 +204,7 @@ def main():
     scale = float(np.abs(A).max())
     pd = _abi.Problem(m, n, m, int(mx), dA.data_ptr(), db.data_ptr(), dc.data_ptr())
     stream = torch.cuda.current_stream()
-    opt = _abi.Options(-1.0, -1.0, lo, hi, 0, algo, None, stream.cuda_stream)
+    opt = _abi.Options(-1.0, -1.0, lo, hi, 0, algo, None, stream.cuda_stream, rank if world > 1 else 0, world if world > 1 else 0)
     part = torch.zeros(256, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(world * 256, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -253,7 +254,9 @@ def main():
     wall = max_over_ranks(time.perf_counter() - t0)
     launches_per_step = nl.value + 2                 # + flush fill + gather/copy
     kern_ms = [a.elapsed_time(bb) for a, bb in ev]   # this rank's enumeration launches (CUDA events, same stream)
-    kern_ms_mean = max_over_ranks(float(np.mean(kern_ms)))
+    kern_ms_own = float(np.mean(kern_ms))
+    kern_ms_mean = max_over_ranks(kern_ms_own)
+    own_bases = _abi.Partial.from_buffer_copy(part.cpu().numpy().tobytes()).n_bases
     res = merged_result()
     value = total * args.steps / wall
 
@@ -264,7 +267,8 @@ def main():
     g6 = torch.zeros(world * 6, dtype=torch.float64, device=dev)
 
     def step_e2e():
-        r = solver.enumerate(rank_begin=lo, rank_end=hi)       # H2D(A,b,c,binom) + kernels + D2H(256 B)
+        r = solver.enumerate(rank_begin=lo, rank_end=hi, shard_index=rank if world > 1 else 0,
+                             shard_count=world if world > 1 else 0)       # H2D(A,b,c,binom) + kernels + D2H(256 B)
         if world > 1:
             pinned[0] = r.key; pinned[1] = float(r.best_rank); pinned[2] = r.n_singular
             pinned[3] = r.n_infeasible; pinned[4] = r.n_feasible; pinned[5] = r.objective
@@ -301,14 +305,14 @@ def main():
         pass
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     nominal = 148 * 64 * 2 * sm_max * 1e6 / 1e12
-    shard = hi - lo
-    achieved = shard * F / (kern_ms_mean * 1e-3) / 1e12
+    shard = own_bases                           # bases this rank's launch visited
+    achieved = shard * F / (kern_ms_own * 1e-3) / 1e12
     roofline = {"bound": "fp64", "achieved": achieved, "peak": probe, "unit": "TFLOP/s",
                 "frac": achieved / probe if probe > 0 else None, "traffic": None,
                 "peak_source": "in-run register-resident DFMA-chain probe (enumgpu_fp64_peak_tflops); "
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
-                "flops_per_basis": F, "bases_per_launch": shard, "launch_ms": kern_ms_mean,
+                "flops_per_basis": F, "bases_per_launch": shard, "launch_ms": kern_ms_own, "launch_ms_max_over_ranks": kern_ms_mean,
                 "kernel": "k_shared" if res.algo_used == _abi.ALGO_SHARED else "k_independent",
                 "note": "algorithmic flops (one dgesv + dot per basis); the shared-prefix kernel executes fewer — see DESIGN.md §6"}
 

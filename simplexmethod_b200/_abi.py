@@ -38,6 +38,7 @@ class Options(C.Structure):
         ("n_devices", C.c_int32), ("algo", C.c_int32),
         ("devices", C.POINTER(C.c_int32)),
         ("stream", C.c_void_p),
+        ("shard_index", C.c_int32), ("shard_count", C.c_int32),
     ]
 
 

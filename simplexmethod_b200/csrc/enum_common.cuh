@@ -33,6 +33,8 @@ struct LaunchParams {
     double   thr;           // eps_piv * max|A_ij|
     uint64_t rank_begin, rank_end;
     uint32_t chunk;         // ranks per thread (independent kernel)
+    uint32_t shard_index;   // interleaved sharding: this launch owns the work
+    uint32_t shard_count;   // windows whose index is shard_index mod shard_count
 };
 
 // (key, rank) pair + counters: what every thread / warp / block / GPU reduces.

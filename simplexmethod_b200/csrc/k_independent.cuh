@@ -130,7 +130,8 @@ k_independent(const LaunchParams prm, BlockPartial* __restrict__ partials)
     uint64_t best_rank = ~0ull;
     uint32_t ns = 0, ni = 0, nf = 0;
 
-    const uint64_t gtid = (uint64_t)blockIdx.x * kIndepThreads + threadIdx.x;
+    // block-granular windows dealt round-robin to the shards
+    const uint64_t gtid = ((uint64_t)blockIdx.x * prm.shard_count + prm.shard_index) * kIndepThreads + threadIdx.x;
     uint64_t r0 = prm.rank_begin + gtid * prm.chunk;
     if (r0 < prm.rank_end) {
         uint64_t r1 = r0 + prm.chunk;
@@ -180,7 +181,7 @@ k_independent_generic(const LaunchParams prm, BlockPartial* __restrict__ partial
     double   best_key = __longlong_as_double(0x7ff0000000000000LL);
     uint64_t best_rank = ~0ull;
     uint32_t ns = 0, ni = 0, nf = 0;
-    const uint64_t gtid = (uint64_t)blockIdx.x * kIndepThreads + threadIdx.x;
+    const uint64_t gtid = ((uint64_t)blockIdx.x * prm.shard_count + prm.shard_index) * kIndepThreads + threadIdx.x;
     const uint64_t r0 = prm.rank_begin + gtid * prm.chunk;
     if (r0 < prm.rank_end) {
         uint64_t r1 = r0 + prm.chunk;

@@ -137,15 +137,18 @@ class EnumerationSolver:
             x[res.basis[i]] = res.x_B[i]
         return x[: p.GetOriginalVariablesCount()].copy()
 
-    def enumerate(self, rank_begin: int = 0, rank_end: int = 0) -> _abi.Result:
-        """Run the enumeration and return the raw result struct (no exception on NO_FEASIBLE)."""
+    def enumerate(self, rank_begin: int = 0, rank_end: int = 0, shard_index: int = 0, shard_count: int = 0) -> _abi.Result:
+        """Run the enumeration and return the raw result struct (no exception on NO_FEASIBLE).
+
+        shard_index/shard_count select the interleaved rank windows of one shard
+        (one process per GPU); the partial results merge with enumgpu_merge_partial."""
         p = self._problem
         A, b, c = p.GetConstraintsMatrix(), p.GetRightHandSide(), p.GetObjectiveCoefficients()
         ps = _problem_struct(A, b, c, p.IsMaximization())
         nd = 0 if self._devices is None else len(self._devices)
         dev = (C.c_int32 * max(nd, 1))(*(self._devices or [0]))
         o = _abi.Options(self._eps[0], self._eps[1], rank_begin, rank_end, nd, self._algo,
-                         C.cast(dev, C.POINTER(C.c_int32)) if nd else None, None)
+                         C.cast(dev, C.POINTER(C.c_int32)) if nd else None, None, shard_index, shard_count)
         res = _abi.Result()
         rc = lib().enumgpu_solve(C.byref(ps), C.byref(o), C.byref(res))
         _check(rc)

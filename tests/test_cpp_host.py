@@ -55,9 +55,12 @@ def test_python_canonical_per_basis_methods(gpu_lib, oracle):
     can = sm.Canonical(A, b, c, [2, 3])
     assert can.GetBasicSolution().tolist() == [0.0, 0.0, 5.0, 6.0] and can.IsFeasibleBasis()
     assert not sm.Canonical(A, b, c, [0, 3]).IsFeasibleBasis()               # infeasible
-    x = sm.Canonical(A, b, c, [3, 1]).GetBasicSolution()                     # unsorted basis order
-    st, xo, _ = oracle.eval_basis(A[:, [3, 1]], b, c[[3, 1]], False, [0, 1])
-    assert st == 0 and [x[3], x[1]] == xo
+    for basis, want in (([2, 1], 0), ([3, 1], 1)):                           # unsorted order; feasible / infeasible
+        can2 = sm.Canonical(A, b, c, basis)
+        x = can2.GetBasicSolution()                                          # returned whether feasible or not
+        st, xo, _ = oracle.eval_basis(A[:, basis], b, c[basis], False, [0, 1])
+        assert st == want and [x[basis[0]], x[basis[1]]] == xo
+        assert can2.IsFeasibleBasis() == (want == 0)
     A2, b2, c2, mx = lpgen.main_cpp_canonical()
     with pytest.raises(RuntimeError, match="Singular"):
         sm.Canonical(A2, b2, c2, [2, 3], minimize=False).GetBasicSolution()  # duplicate columns

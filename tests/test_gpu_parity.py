@@ -227,3 +227,22 @@ def test_multi_device_in_process(gpu_lib, oracle):
     for devs in ([0], [0, 0, 0], list(range(nd))):
         res = gpu_solve(A, b, c, mx, devices=devs)
         assert_same(res, o, 8)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_interleaved_shards_merge_to_full(gpu_lib, oracle, algo, shards):
+    """enumgpu_options.shard_index/shard_count: the shards tile the range exactly and merge to the full result."""
+    A, b, c, mx = lpgen.dense_lp(8, 24, 3)
+    o, _ = oracle.solve(A, b, c, mx, n_threads=os.cpu_count())
+    can = sm.Canonical(A, b, c, list(range(8)), minimize=not mx)
+    for (lo, hi) in ((0, 0), (12345, 700001)):
+        if (lo, hi) != (0, 0):
+            o, _ = oracle.solve(A, b, c, mx, n_threads=os.cpu_count(), rank_begin=lo, rank_end=hi)
+        parts = [sm.EnumerationSolver(can, algo=algo).enumerate(lo, hi, shard_index=i, shard_count=shards) for i in range(shards)]
+        assert sum(p.n_bases for p in parts) == o.n_bases
+        assert sum(p.n_feasible for p in parts) == o.n_feasible and sum(p.n_infeasible for p in parts) == o.n_infeasible
+        best = min((p.key, p.best_rank) for p in parts if p.status == 0)
+        assert best == (o.key, o.best_rank)
+    with pytest.raises(ValueError):
+        sm.EnumerationSolver(can).enumerate(shard_index=3, shard_count=3)
