@@ -4,8 +4,7 @@
 // methods, GetBasicSolution and IsFeasibleBasis (reference Canonical.cpp:165-197,
 // Eigen ColPivHouseholderQR on the host), are served by libenumgpu's
 // enumgpu_eval_basis on the GPU with the frozen GE arithmetic.
-// Not carried over: ToCommon / ToSymmetrical / GetDual (off the enumeration
-// path; SURVEY.md §8 marks them out of scope / "next").
+// Not carried over: ToCommon / ToSymmetrical (off the enumeration path).
 #pragma once
 
 #include <memory>
@@ -36,6 +35,10 @@ public:
     // SimplexSolover.h:124-126) or no CUDA device is available.
     Eigen::VectorXd GetBasicSolution() const;
     bool IsFeasibleBasis() const;
+
+    // Canonical form of the dual as the reference builds it (Canonical.cpp:305-364):
+    // [A' | -A' | I], right-hand side c, costs [b | -b | 0], slack basis, opposite sense.
+    std::unique_ptr<Canonical> GetDual() const;
 
 private:
     Eigen::MatrixXd A_;

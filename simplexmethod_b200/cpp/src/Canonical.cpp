@@ -78,3 +78,23 @@ bool Canonical::IsFeasibleBasis() const
     double z = 0.0;
     return eval_designated_basis(*this, xB, z) == ENUMGPU_BASIS_FEASIBLE;
 }
+
+std::unique_ptr<Canonical> Canonical::GetDual() const
+{
+    const auto m = A_.rows(), n = A_.cols();
+    Eigen::MatrixXd Ad(n, 2 * m + n);
+    Eigen::VectorXd cd = Eigen::VectorXd::Zero(2 * m + n);
+    for (Eigen::Index j = 0; j < n; ++j) {
+        for (Eigen::Index i = 0; i < m; ++i) {
+            Ad(j, i) = A_(i, j);            // y'
+            Ad(j, m + i) = -A_(i, j);       // y''
+        }
+        Ad(j, 2 * m + j) = 1.0;             // slack of dual row j
+    }
+    for (Eigen::Index i = 0; i < m; ++i) { cd[i] = b_[i]; cd[m + i] = -b_[i]; }
+    std::vector<int> basis(static_cast<size_t>(n));
+    for (Eigen::Index j = 0; j < n; ++j) basis[static_cast<size_t>(j)] = static_cast<int>(2 * m + j);
+    auto dual = std::make_unique<Canonical>(Ad, c_, cd, basis, !minimize_);
+    dual->SetOriginalVariablesCount(static_cast<int>(2 * m));
+    return dual;
+}

@@ -45,6 +45,14 @@ int main()
     copy.SetOriginalVariablesCount(2);
     CHECK(can.GetOriginalVariablesCount() == 4 && copy.GetOriginalVariablesCount() == 2);
 
+    {   // dual of the canonical fixture: 4 rows x (2*2 + 4) columns, max, slack basis (Canonical.cpp:305-364)
+        auto d = can.GetDual();
+        CHECK(d->GetConstraintsMatrix().rows() == 4 && d->GetConstraintsMatrix().cols() == 8 && d->IsMaximization());
+        CHECK(d->GetConstraintsMatrix()(1, 0) == 2.0 && d->GetConstraintsMatrix()(1, 2) == -2.0 && d->GetConstraintsMatrix()(1, 5) == 1.0);
+        CHECK(d->GetRightHandSide()[1] == 8.0 && d->GetObjectiveCoefficients()[0] == 5.0 && d->GetObjectiveCoefficients()[3] == -6.0);
+        CHECK(d->GetBasisIndices()[0] == 4 && d->GetOriginalVariablesCount() == 4);
+    }
+
     // --- Symmetrical -> Canonical (tests/test_symmetrical.cpp:64-71, 83-84) and the dual (:47-52)
     const Eigen::MatrixXd As = mat(2, 2, {1, 2, 3, 4});
     Eigen::VectorXd bs(2); bs[0] = 5; bs[1] = 6;

@@ -68,6 +68,21 @@ class Canonical:
         return float(self._c @ x)
 
 
+    def GetDual(self) -> "Canonical":
+        """Canonical form of the dual, built like the reference (Canonical.cpp:305-364):
+        variables y = y' - y'' and one slack per dual row: A_d = [A' | -A' | I] (n x (2m+n)),
+        b_d = c, c_d = [b | -b | 0], slack basis, opposite sense, 2m original variables.
+        (Like the reference's, the construction is the dual of a MIN primal.)"""
+        m, n = self._A.shape
+        Ad = np.zeros((n, 2 * m + n), order="F")
+        Ad[:, :m] = self._A.T
+        Ad[:, m:2 * m] = -self._A.T
+        Ad[:, 2 * m:] = np.eye(n)
+        cd = np.concatenate([self._b, -self._b, np.zeros(n)])
+        dual = Canonical(Ad, self._c.copy(), cd, [2 * m + i for i in range(n)], minimize=not self._minimize)
+        dual.SetOriginalVariablesCount(2 * m)
+        return dual
+
     # -- per-basis numerics: on the GPU, through enumgpu_eval_basis ---------
     def _eval_designated(self):
         ps = _problem_struct(self._A, self._b, self._c, not self._minimize)

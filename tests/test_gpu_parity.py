@@ -246,3 +246,26 @@ def test_interleaved_shards_merge_to_full(gpu_lib, oracle, algo, shards):
         assert best == (o.key, o.best_rank)
     with pytest.raises(ValueError):
         sm.EnumerationSolver(can).enumerate(shard_index=3, shard_count=3)
+
+
+@pytest.mark.parametrize("name", ["test_canonical", "beale", "dense36"])
+def test_strong_duality_by_enumeration(gpu_lib, oracle, name):
+    """Lab step 5 / SURVEY N4: enumerate the primal and its dual (Canonical.GetDual, as the reference
+    builds it) with the same kernel; optimal objectives coincide (strong duality)."""
+    if name == "dense36":
+        A, b, c, mx = lpgen.dense_lp(3, 6, 5)
+    else:
+        g = GOLD[name]
+        A, b, c, mx = np.array(g["A"]), np.array(g["b"]), np.array(g["c"]), g["maximize"]
+    assert not mx
+    m, n = A.shape
+    primal = sm.Canonical(A, b, c, list(range(m)), minimize=True)
+    dual = primal.GetDual()
+    assert dual.GetConstraintsMatrix().shape == (n, 2 * m + n) and dual.IsMaximization()
+    sp_, sd_ = sm.EnumerationSolver(primal), sm.EnumerationSolver(dual)
+    sp_.solve(); y2 = sd_.solve()
+    assert sd_.objective() == pytest.approx(sp_.objective(), rel=1e-9, abs=1e-9)
+    y = y2[:m] - y2[m:]                                   # y = y' - y''
+    assert np.all(A.T @ y <= c + 1e-9)                    # dual feasibility
+    od, _ = oracle.solve(dual.GetConstraintsMatrix(), dual.GetRightHandSide(), dual.GetObjectiveCoefficients(), True, n_threads=4)
+    assert (sd_.bestRank(), sd_.feasibleCount(), sd_.singularCount()) == (od.best_rank, od.n_feasible, od.n_singular)
