@@ -54,3 +54,41 @@ for key, (c, s, w, wi) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
 print()
 for op, (c, s) in sorted(opagg.items(), key=lambda kv: -kv[1][0])[:28]:
     print(f"{op:10s} {100*c/tot:5.1f}% inst {100*s/tsamp:5.1f}% samp")
+
+# ---- executed instructions by kernel region (markers in k_shared.cuh) ------
+try:
+    ksrc = open(os.path.join(root, "simplexmethod_b200", "csrc", "k_shared.cuh")).read().split("\n")
+    marks = []
+    keys = (("__device__ __noinline__ void drain_fn", "drain_fn"), ("k_shared(const SharedParams sp", "prologue"),
+            ("------------- unit loop", "unit start (unrank, align)"), ("---- level Q from A", "level q from A"),
+            ("---- level Q+1 (parent)", "parent level"), ("---- children of this parent", "child level"),
+            ("--------- leaves ---", "item setup (a,b,c)"), ("---- the shared loop over the last column", "d loop"),
+            ("---- next child of the same parent", "next child / parent"), ("--------- reduction", "reduction"), ("// host side", "host"))
+    for i, l in enumerate(ksrc, 1):
+        for k, name in keys:
+            if k in l:
+                marks.append((i, name))
+    marks.sort()
+    def region(ln):
+        r = "helpers"
+        for i, name in marks:
+            if ln >= i:
+                r = name
+        return r
+    # attribute instructions of inlined helpers to the region of the last k_shared.cuh line >= first marker
+    reg_inst, reg_samp, last = {}, {}, "helpers"
+    first_mark = marks[0][0] if marks else 0
+    for r in rows[hi + 1:]:
+        if len(r) <= ix or not r[ix].isdigit():
+            continue
+        off = int(r[ia], 16) - base
+        key = addr2line.get(off)
+        if key and key[0] == "k_shared.cuh" and key[1] >= first_mark:
+            last = region(key[1])
+        reg_inst[last] = reg_inst.get(last, 0) + int(r[ix])
+        reg_samp[last] = reg_samp.get(last, 0) + (int(r[isamp]) if r[isamp].isdigit() else 0)
+    print("\nby region (helper instructions attributed to the enclosing region):")
+    for k, v in sorted(reg_inst.items(), key=lambda kv: -kv[1]):
+        print(f"  {k:32s} {100*v/tot:5.1f}% inst {100*reg_samp[k]/tsamp:5.1f}% samp")
+except Exception as ex:  # pragma: no cover
+    print("region breakdown unavailable:", ex)
