@@ -269,3 +269,20 @@ def test_strong_duality_by_enumeration(gpu_lib, oracle, name):
     assert np.all(A.T @ y <= c + 1e-9)                    # dual feasibility
     od, _ = oracle.solve(dual.GetConstraintsMatrix(), dual.GetRightHandSide(), dual.GetObjectiveCoefficients(), True, n_threads=4)
     assert (sd_.bestRank(), sd_.feasibleCount(), sd_.singularCount()) == (od.best_rank, od.n_feasible, od.n_singular)
+
+
+def test_shared_kernel_range_guard(gpu_lib, oracle):
+    """eps_piv = 0 (or absurd scaling) takes the branch-free reciprocal of k_shared out of its proven range:
+    the library must fall back to the independent kernel, and still match the oracle."""
+    A, b, c, mx = lpgen.dense_lp(7, 16, 9)
+    can = sm.Canonical(A, b, c, list(range(7)), minimize=not mx)
+    res = sm.EnumerationSolver(can, algo=_abi.ALGO_SHARED, eps_piv=0.0).enumerate()
+    o, _ = oracle.solve(A, b, c, mx, eps_piv=0.0)
+    assert res.algo_used == _abi.ALGO_INDEPENDENT
+    assert_same(res, o, 7)
+    tiny = sm.Canonical(A * 1e-295, b * 1e-295, c, list(range(7)), minimize=not mx)
+    res = sm.EnumerationSolver(tiny, algo=_abi.ALGO_SHARED).enumerate()
+    o, _ = oracle.solve(A * 1e-295, b * 1e-295, c, mx)
+    assert res.algo_used == _abi.ALGO_INDEPENDENT
+    assert_same(res, o, 7)
+    assert sm.EnumerationSolver(can, algo=_abi.ALGO_SHARED).enumerate().algo_used == _abi.ALGO_SHARED
