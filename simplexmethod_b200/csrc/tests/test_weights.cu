@@ -1,0 +1,78 @@
+// test_weights.cu — host-only check of the work-window arithmetic of k_shared.cuh
+// (weight_unrank / weight_of_child / subtree_weight): the device walks exactly
+// these functions, so the windows tile the child tasks iff these are consistent.
+//   * child intervals are contiguous and in lexicographic order;
+//   * weight_unrank inverts weight_of_child anywhere inside an interval and
+//     reports the interval's header;
+//   * the total equals the sum of the level-0 subtrees.
+// Exit code 0 = all passed.  Needs no GPU.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../k_shared.cuh"
+
+using namespace enumgpu;
+
+static uint64_t binom(int top, int k)
+{
+    if (top < 0 || k < 0 || k > top) return 0;
+    unsigned __int128 r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (unsigned)(top - k + i) / (unsigned)i;
+    return (uint64_t)r;
+}
+
+#define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "FAILED %s:%d: %s  (n=%d m=%d)\n", __FILE__, __LINE__, #c, n, m); return 1; } } while (0)
+
+static int run(int n, int m)
+{
+    auto C = [](int top, int k) -> uint64_t { return binom(top, k); };
+    const int P = m - kT, Q = P - 2;
+    std::vector<int> S(P), T(kMaxM);
+    for (int i = 0; i < P; ++i) S[i] = i;
+    uint64_t expect = 0, n_children = 0, bases = 0;
+    for (;;) {
+        // header of this child: first child of its parent (+ first parent of its depth-q node)
+        uint32_t hdr = 0;
+        const bool first_child = (P >= 2) ? (S[P - 1] == S[P - 2] + 1) : false;
+        if (first_child) {
+            hdr += kWParent;
+            bool first_parent = true;
+            for (int j = Q; j < P - 1; ++j) first_parent &= (j == 0) ? false : (S[j] == S[j - 1] + 1);
+            if (Q >= 1 && first_parent) hdr += kWNode;
+        }
+        const uint64_t leaves = binom(n - 1 - S[P - 1], kT);
+        const uint64_t w = weight_of_child(C, n, m, S.data());
+        CHECK(w == expect);
+        uint64_t off; uint32_t h;
+        const uint64_t probes[3] = {0, (hdr + kWChild + leaves) / 2, hdr + kWChild + leaves - 1};
+        for (uint64_t pr : probes) {
+            weight_unrank(C, n, m, w + pr, T.data(), &off, &h);
+            for (int i = 0; i < P; ++i) CHECK(T[i] == S[i]);
+            CHECK(off == pr);
+            CHECK(h == hdr);
+        }
+        expect += hdr + kWChild + leaves;
+        ++n_children; bases += leaves;
+        int i = P - 1;                                         // next valid prefix
+        while (i >= 0 && S[i] == n - m + i) --i;
+        if (i < 0) break;
+        ++S[i];
+        for (int j = i + 1; j < P; ++j) S[j] = S[j - 1] + 1;
+    }
+    uint64_t total = 0;
+    for (int v = 0; v <= n - m; ++v) total += subtree_weight(C, n, m, 0, v);
+    CHECK(total == expect);
+    CHECK(bases == binom(n, m));
+    CHECK(n_children == binom(n - kT, P));
+    return 0;
+}
+
+int main()
+{
+    const int cases[][2] = {{6, 6}, {9, 6}, {12, 7}, {13, 8}, {16, 9}, {15, 10}, {18, 12}, {20, 16}, {24, 8}};
+    for (auto& c : cases)
+        if (run(c[0], c[1])) return 1;
+    std::puts("test_weights: all passed");
+    return 0;
+}

@@ -126,3 +126,13 @@ def test_product_package_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 for needle in ("libenumcpu", "enumcpu.h", "enumcpu_", "from oracle", "import oracle", "oracle/_ref"):
                     assert needle not in text, f"{f} references the oracle ({needle})"
+
+
+def test_work_window_arithmetic_host():
+    """k_shared's cost-weighted work windows: weight_unrank inverts weight_of_child, intervals are contiguous
+    (simplexmethod_b200/csrc/tests/test_weights.cu, host-only build of the functions the device walks)."""
+    csrc = os.path.join(ROOT, "simplexmethod_b200", "csrc")
+    subprocess.check_call(["make", "-C", csrc, "-s", "tests/test_weights"])
+    out = subprocess.run([os.path.join(csrc, "tests", "test_weights")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "all passed" in out.stdout
