@@ -286,3 +286,14 @@ def test_shared_kernel_range_guard(gpu_lib, oracle):
     assert res.algo_used == _abi.ALGO_INDEPENDENT
     assert_same(res, o, 7)
     assert sm.EnumerationSolver(can, algo=_abi.ALGO_SHARED).enumerate().algo_used == _abi.ALGO_SHARED
+
+
+@pytest.mark.parametrize("m,n,seed", [(6, 64, 3), (8, 40, 4), (16, 20, 5), (9, 33, 6)])
+def test_wide_and_tall_shapes_shared_kernel(gpu_lib, oracle, m, n, seed):
+    """Limits of the shared kernel: n = ENUMGPU_MAX_N (two columns per lane in the level code, fewer warps per
+    CTA), m = ENUMGPU_MAX_M, and a shape where one child task has more than 32 candidate columns."""
+    A, b, c, mx = lpgen.dense_lp(m, n, seed)
+    res = gpu_solve(A, b, c, mx, _abi.ALGO_SHARED)
+    assert res.algo_used == _abi.ALGO_SHARED
+    o, _ = oracle.solve(A, b, c, mx, n_threads=os.cpu_count())
+    assert_same(res, o, m)
