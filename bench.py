@@ -311,7 +311,7 @@ def main():
                 "frac": achieved / probe if probe > 0 else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one k_shared<12> launch over the full
                 # C(40,12) range, from the ncu --set full capture under profiles/ (r1_k_shared_m12n40_ncu_key_metrics.csv)
-                "traffic": 772352 if (m, n, world) == (12, 40, 1) and res.algo_used == _abi.ALGO_SHARED else None,
+                "traffic": 798720 if (m, n, world) == (12, 40, 1) and res.algo_used == _abi.ALGO_SHARED else None,
                 "traffic_unit": "bytes per launch (algorithmic input: 13 KB; the rest is instruction fetch, tables, spill write-back)",
                 "peak_source": "in-run register-resident DFMA-chain probe (enumgpu_fp64_peak_tflops); "
                                "MEASURED_PEAKS.json has no FP64 figure",
