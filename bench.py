@@ -252,7 +252,8 @@ def main():
         edist.all_gather_records(part, gathered, world)
     barrier()
     wall = max_over_ranks(time.perf_counter() - t0)
-    launches_per_step = nl.value + 2                 # + flush fill + gather/copy
+    launches_per_step = nl.value                     # kernels of libenumgpu per step (the L2-flush fill and the
+                                                     # 256-byte copy / NCCL all-gather are torch's and not counted)
     kern_ms = [a.elapsed_time(bb) for a, bb in ev]   # this rank's enumeration launches (CUDA events, same stream)
     kern_ms_own = float(np.mean(kern_ms))
     kern_ms_mean = max_over_ranks(kern_ms_own)
