@@ -42,17 +42,18 @@ static int run(int n, int m)
             if (Q >= 1 && first_parent) hdr += kWNode;
         }
         const uint64_t leaves = binom(n - 1 - S[P - 1], kT);
+        const uint32_t wchild = (S[P - 1] >= n - kTailR) ? kWTailChild : kWChild;   // pooled tail children are cheaper
         const uint64_t w = weight_of_child(C, n, m, S.data());
         CHECK(w == expect);
         uint64_t off; uint32_t h;
-        const uint64_t probes[3] = {0, (hdr + kWChild + leaves) / 2, hdr + kWChild + leaves - 1};
+        const uint64_t probes[3] = {0, (hdr + wchild + leaves) / 2, hdr + wchild + leaves - 1};
         for (uint64_t pr : probes) {
             weight_unrank(C, n, m, w + pr, T.data(), &off, &h);
             for (int i = 0; i < P; ++i) CHECK(T[i] == S[i]);
             CHECK(off == pr);
             CHECK(h == hdr);
         }
-        expect += hdr + kWChild + leaves;
+        expect += hdr + wchild + leaves;
         ++n_children; bases += leaves;
         int i = P - 1;                                         // next valid prefix
         while (i >= 0 && S[i] == n - m + i) --i;
@@ -70,7 +71,7 @@ static int run(int n, int m)
 
 int main()
 {
-    const int cases[][2] = {{6, 6}, {9, 6}, {12, 7}, {13, 8}, {16, 9}, {15, 10}, {18, 12}, {20, 16}, {24, 8}};
+    const int cases[][2] = {{6, 6}, {9, 6}, {12, 7}, {13, 8}, {16, 9}, {15, 10}, {18, 12}, {20, 16}, {24, 8}, {22, 9}};
     for (auto& c : cases)
         if (run(c[0], c[1])) return 1;
     std::puts("test_weights: all passed");
