@@ -297,3 +297,27 @@ def test_wide_and_tall_shapes_shared_kernel(gpu_lib, oracle, m, n, seed):
     assert res.algo_used == _abi.ALGO_SHARED
     o, _ = oracle.solve(A, b, c, mx, n_threads=os.cpu_count())
     assert_same(res, o, m)
+
+
+def test_beyond_headline_size_properties(gpu_lib):
+    """m=12, n=44 (21 090 682 613 bases, too many for the CPU oracle): size-independent properties —
+    every rank falls in exactly one class, the optimum is HiGHS's, B x_B = b, and the result is the same for
+    both kernel-independent shardings (1 shard vs 3 interleaved shards merged)."""
+    from scipy.optimize import linprog
+    m, n = 12, 44
+    A, b, c, mx = lpgen.dense_lp(m, n, 7)
+    can = sm.Canonical(A, b, c, list(range(m)), minimize=not mx)
+    s = sm.EnumerationSolver(can)
+    x = s.solve()
+    total = gpu_lib.enumgpu_binomial(n, m)
+    assert s.basesEvaluated() == total == 21090682613
+    assert s.singularCount() + s.infeasibleCount() + s.feasibleCount() == total
+    h = linprog(c, A_eq=A, b_eq=b, bounds=(0, None), method="highs")
+    assert s.objective() == pytest.approx(h.fun, rel=1e-9)
+    assert sorted(np.nonzero(h.x > 1e-9)[0].tolist()) == s.optimalBasis()
+    assert np.allclose(A[:, s.optimalBasis()] @ np.array(s.basicValues()), b, rtol=0, atol=1e-9)
+    parts = [sm.EnumerationSolver(can).enumerate(shard_index=i, shard_count=3) for i in range(3)]
+    assert sum(p.n_bases for p in parts) == total
+    assert sum(p.n_feasible for p in parts) == s.feasibleCount()
+    assert sum(p.n_singular for p in parts) == s.singularCount()
+    assert min((p.key, p.best_rank) for p in parts if p.status == 0) == (s._res.key, s.bestRank())
