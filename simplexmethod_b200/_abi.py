@@ -81,6 +81,10 @@ SYMBOLS = {
     "enumgpu_solve_device": (C.c_int, [C.POINTER(Problem), C.c_double, C.POINTER(Options), C.POINTER(Result)]),
     "enumgpu_eval_basis": (C.c_int, [C.POINTER(Problem), C.POINTER(Options), C.POINTER(C.c_int32),
                                       C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "enumgpu_list_feasible": (C.c_int, [C.POINTER(Problem), C.POINTER(Options), C.POINTER(C.c_uint64), C.c_uint64,
+                                         C.POINTER(C.c_uint64), C.POINTER(Result)]),
+    "enumgpu_eval_ranks": (C.c_int, [C.POINTER(Problem), C.POINTER(Options), C.POINTER(C.c_uint64), C.c_uint64,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "enumgpu_enqueue_device": (C.c_int, [C.POINTER(Problem), C.c_double, C.POINTER(Options), C.c_void_p,
                                           C.POINTER(C.c_int32)]),
     "enumgpu_partial_to_result": (None, [C.POINTER(Partial), C.POINTER(Result)]),

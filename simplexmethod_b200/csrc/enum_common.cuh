@@ -35,7 +35,18 @@ struct LaunchParams {
     uint32_t chunk;         // ranks per thread (independent kernel)
     uint32_t shard_index;   // interleaved sharding: this launch owns the work
     uint32_t shard_count;   // windows whose index is shard_index mod shard_count
+    // optional listing of the feasible bases (enumgpu_list_feasible): ranks are appended in
+    // arbitrary order; *list_count counts all of them, only the first list_cap are stored
+    unsigned long long* list_count;
+    uint64_t* list_ranks;
+    uint64_t  list_cap;
 };
+
+__device__ __forceinline__ void list_append(unsigned long long* count, uint64_t* ranks, uint64_t cap, uint64_t rank)
+{
+    const unsigned long long pos = atomicAdd(count, 1ull);
+    if (pos < cap) ranks[pos] = rank;
+}
 
 // (key, rank) pair + counters: what every thread / warp / block / GPU reduces.
 struct Best {

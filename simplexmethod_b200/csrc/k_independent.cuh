@@ -150,6 +150,7 @@ k_independent(const LaunchParams prm, BlockPartial* __restrict__ partials)
             else if (st == 1) ++ni;
             else {
                 ++nf;
+                if (prm.list_count) list_append(prm.list_count, prm.list_ranks, prm.list_cap, r);
                 const double key = prm.maximize ? -z : z;
                 if (better(key, r, best_key, best_rank)) { best_key = key; best_rank = r; }
             }
@@ -195,6 +196,7 @@ k_independent_generic(const LaunchParams prm, BlockPartial* __restrict__ partial
             else if (st == 1) ++ni;
             else {
                 ++nf;
+                if (prm.list_count) list_append(prm.list_count, prm.list_ranks, prm.list_cap, r);
                 const double key = prm.maximize ? -z : z;
                 if (better(key, r, best_key, best_rank)) { best_key = key; best_rank = r; }
             }

@@ -170,6 +170,54 @@ class EnumerationSolver:
         self._res = res
         return res
 
+    # -- the extreme points themselves (README step 9 of the reference) -------
+    def listFeasibleBases(self, capacity: int = 1 << 22):
+        """Ranks (ascending, uint64 array) of the feasible bases, at most `capacity` of them; the result
+        struct of the same enumeration is kept (feasibleCount() is the full count)."""
+        p = self._problem
+        ps = _problem_struct(p.GetConstraintsMatrix(), p.GetRightHandSide(), p.GetObjectiveCoefficients(), p.IsMaximization())
+        o = _abi.Options(self._eps[0], self._eps[1], 0, 0, 0, self._algo, None, None, 0, 0)
+        ranks = np.zeros(max(int(capacity), 1), dtype=np.uint64)
+        n_listed = C.c_uint64()
+        res = _abi.Result()
+        rc = lib().enumgpu_list_feasible(C.byref(ps), C.byref(o), ranks.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                         int(capacity), C.byref(n_listed), C.byref(res))
+        _check(rc)
+        self._res = res
+        return ranks[: n_listed.value].copy()
+
+    def evaluateBases(self, ranks):
+        """(bases [k, m] int, x_B [k, m], objective [k], class [k]) of the bases with the given ranks, on the GPU."""
+        p = self._problem
+        A = p.GetConstraintsMatrix()
+        m, n = A.shape
+        ranks = np.ascontiguousarray(np.asarray(ranks, dtype=np.uint64))
+        k = ranks.size
+        xB = np.zeros((k, m)); z = np.zeros(k); cls = np.zeros(k, dtype=np.int32)
+        ps = _problem_struct(A, p.GetRightHandSide(), p.GetObjectiveCoefficients(), p.IsMaximization())
+        o = _abi.Options(self._eps[0], self._eps[1], 0, 0, 0, self._algo, None, None, 0, 0)
+        _check(lib().enumgpu_eval_ranks(C.byref(ps), C.byref(o), ranks.ctypes.data_as(C.POINTER(C.c_uint64)), k,
+                                        xB.ctypes.data_as(C.POINTER(C.c_double)), z.ctypes.data_as(C.POINTER(C.c_double)),
+                                        cls.ctypes.data_as(C.POINTER(C.c_int32))))
+        bases = np.zeros((k, m), dtype=np.int32)
+        buf = (C.c_int32 * m)()
+        for i, r in enumerate(ranks):
+            lib().enumgpu_unrank(n, m, int(r), buf)
+            bases[i] = buf[:]
+        return bases, xB, z, cls
+
+    def feasibleVertices(self, capacity: int = 1 << 20, decimals: int = 9):
+        """Distinct feasible vertices x (rows, length n) and their objective values: degenerate vertices are
+        reached by several bases; rows are merged when they agree to `decimals` digits (host-side grouping)."""
+        ranks = self.listFeasibleBases(capacity)
+        bases, xB, z, _ = self.evaluateBases(ranks)
+        n = self._problem.GetObjectiveCoefficients().size
+        X = np.zeros((ranks.size, n))
+        np.put_along_axis(X, bases.astype(np.int64), xB, axis=1)
+        _, first = np.unique(np.round(X, decimals) + 0.0, axis=0, return_index=True)
+        first.sort()
+        return X[first], z[first]
+
     # -- accessors the parity metric needs (not in the reference) -----------
     def _need(self) -> _abi.Result:
         if self._res is None:

@@ -321,3 +321,31 @@ def test_beyond_headline_size_properties(gpu_lib):
     assert sum(p.n_feasible for p in parts) == s.feasibleCount()
     assert sum(p.n_singular for p in parts) == s.singularCount()
     assert min((p.key, p.best_rank) for p in parts if p.status == 0) == (s._res.key, s.bestRank())
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_list_feasible_bases_and_vertices(gpu_lib, oracle, algo):
+    """enumgpu_list_feasible / enumgpu_eval_ranks: the extreme points themselves.  Ranks == the oracle's
+    per-rank classification; x_B of every listed basis == the oracle's; vertices of the lab LP == SURVEY A.1."""
+    A, b, c, mx = lpgen.dense_lp(8, 20, 5)
+    o, status = oracle.solve(A, b, c, mx, want_status=True)
+    want = np.nonzero(status == 0)[0]
+    s = sm.EnumerationSolver(sm.Canonical(A, b, c, list(range(8)), minimize=not mx), algo=algo)
+    ranks = s.listFeasibleBases()
+    assert ranks.tolist() == want.tolist() and s.feasibleCount() == want.size and s.bestRank() == o.best_rank
+    few = s.listFeasibleBases(capacity=10)                       # too small: some 10 of them, ascending
+    assert few.size == 10 and set(few.tolist()) <= set(want.tolist()) and (np.diff(few.astype(np.int64)) > 0).all()
+    assert s.feasibleCount() == want.size
+    bases, xB, z, cls = s.evaluateBases(ranks[:50])
+    assert (cls == 0).all()
+    for i in range(50):
+        st, xo, zo = oracle.eval_basis(A, b, c, mx, bases[i].tolist())
+        assert st == 0 and xB[i].tolist() == xo and z[i] == zo
+    _, _, _, cls_mixed = s.evaluateBases([0, 1, 2, int(want[0])])
+    assert cls_mixed.tolist() == [int(status[0]), int(status[1]), int(status[2]), 0]
+    # the reference's lab LP: 7 feasible bases, 4 distinct vertices (SURVEY A.1)
+    A, b, c, mx = lpgen.lab_symmetric_canonical()
+    s = sm.EnumerationSolver(sm.Canonical(A, b, c, [3, 4], minimize=False), algo=algo)
+    assert s.listFeasibleBases().tolist() == [1, 2, 4, 5, 7, 8, 9]
+    X, zz = s.feasibleVertices()
+    assert X.shape == (4, 5) and sorted(np.round(zz, 9).tolist()) == [0.0, 10.0, 32.0, 35.0]
