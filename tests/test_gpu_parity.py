@@ -349,3 +349,28 @@ def test_list_feasible_bases_and_vertices(gpu_lib, oracle, algo):
     assert s.listFeasibleBases().tolist() == [1, 2, 4, 5, 7, 8, 9]
     X, zz = s.feasibleVertices()
     assert X.shape == (4, 5) and sorted(np.round(zz, 9).tolist()) == [0.0, 10.0, 32.0, 35.0]
+
+
+def test_reentrant_from_two_host_threads(gpu_lib, oracle):
+    """The ABI promises re-entrancy (no global mutable state but a thread-local error string): two host
+    threads enumerate different LPs at the same time, repeatedly, and both get the oracle's answers."""
+    import threading
+    lps = [lpgen.dense_lp(8, 22, 11), lpgen.dense_lp(9, 21, 12)]
+    want = [oracle.solve(*lp, n_threads=4)[0] for lp in lps]
+    errors = []
+
+    def work(i):
+        try:
+            A, b, c, mx = lps[i]
+            for _ in range(5):
+                res = gpu_solve(A, b, c, mx)
+                assert_same(res, want[i], A.shape[0])
+        except BaseException as e:       # noqa: BLE001 - reported to the main thread
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
