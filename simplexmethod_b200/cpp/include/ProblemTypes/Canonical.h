@@ -4,7 +4,6 @@
 // methods, GetBasicSolution and IsFeasibleBasis (reference Canonical.cpp:165-197,
 // Eigen ColPivHouseholderQR on the host), are served by libenumgpu's
 // enumgpu_eval_basis on the GPU with the frozen GE arithmetic.
-// Not carried over: ToCommon / ToSymmetrical (off the enumeration path).
 #pragma once
 
 #include <memory>
@@ -12,6 +11,7 @@
 
 #include "IProblem.h"
 
+class Common;
 class Symmetrical;
 
 class Canonical : public IProblem {
@@ -39,6 +39,12 @@ public:
     // Canonical form of the dual as the reference builds it (Canonical.cpp:305-364):
     // [A' | -A' | I], right-hand side c, costs [b | -b | 0], slack basis, opposite sense.
     std::unique_ptr<Canonical> GetDual() const;
+
+    // Back to the other forms, original variables only (reference Canonical.cpp:199-303):
+    // ToCommon keeps the rows as equalities; ToSymmetrical replaces each by the
+    // pair (row, -row) with the sense's inequality.
+    std::unique_ptr<Common> ToCommon() const;
+    std::unique_ptr<Symmetrical> ToSymmetrical() const;
 
 private:
     Eigen::MatrixXd A_;

@@ -1,7 +1,6 @@
 // Symmetrical.h — max c'x, Ax <= b, x >= 0  /  min c'x, Ax >= b, x >= 0.
 // Feeds the enumeration path through ToCanonical (reference:
-// src/ProblemTypes/Symmetrical.h:17-45, Symmetrical.cpp:142-223).  ToCommon is
-// not carried over (Common is off the path).
+// src/ProblemTypes/Symmetrical.h:17-45, Symmetrical.cpp:119-273).
 #pragma once
 
 #include <memory>
@@ -9,6 +8,7 @@
 #include "IProblem.h"
 
 class Canonical;
+class Common;
 
 class Symmetrical : public IProblem {
 public:
@@ -23,6 +23,7 @@ public:
 
     std::unique_ptr<Symmetrical> GetDual() const;     // transpose A, swap b and c, flip the sense
     std::unique_ptr<Canonical> ToCanonical() const;   // max: [A | I], slack basis; min: [A | -I | I], artificial basis
+    std::unique_ptr<Common> ToCommon() const;         // same data; rows all <= (max) or >= (min), variables >= 0
 
 private:
     Eigen::MatrixXd A_;

@@ -8,6 +8,8 @@
 #include <stdexcept>
 #include <string>
 
+#include "ProblemTypes/Common.h"
+#include "ProblemTypes/Symmetrical.h"
 #include "enumgpu.h"
 
 Canonical::Canonical(const Eigen::MatrixXd& A, const Eigen::VectorXd& b, const Eigen::VectorXd& c,
@@ -97,4 +99,35 @@ std::unique_ptr<Canonical> Canonical::GetDual() const
     auto dual = std::make_unique<Canonical>(Ad, c_, cd, basis, !minimize_);
     dual->SetOriginalVariablesCount(static_cast<int>(2 * m));
     return dual;
+}
+
+std::unique_ptr<Common> Canonical::ToCommon() const
+{
+    const Eigen::Index m = A_.rows(), n = n_orig_;      // added (slack / surplus / artificial) columns are dropped
+    Eigen::MatrixXd A(m, n);
+    Eigen::VectorXd c(n);
+    for (Eigen::Index j = 0; j < n; ++j) {
+        c[j] = c_[j];
+        for (Eigen::Index i = 0; i < m; ++i) A(i, j) = A_(i, j);
+    }
+    return std::make_unique<Common>(A, b_, c, std::vector<Common::ConstraintType>(static_cast<size_t>(m), Common::ConstraintType::Equal),
+                                    std::vector<Common::VariableType>(static_cast<size_t>(n), Common::VariableType::NonNegative),
+                                    /*maximize=*/!minimize_);
+}
+
+std::unique_ptr<Symmetrical> Canonical::ToSymmetrical() const
+{
+    const Eigen::Index m = A_.rows(), n = n_orig_;
+    Eigen::MatrixXd A(2 * m, n);
+    Eigen::VectorXd b(2 * m), c(n);
+    for (Eigen::Index j = 0; j < n; ++j) c[j] = c_[j];
+    for (Eigen::Index i = 0; i < m; ++i) {              // a'x = b  ->  a'x (<=|>=) b  and  -a'x (<=|>=) -b
+        for (Eigen::Index j = 0; j < n; ++j) {
+            A(2 * i, j) = A_(i, j);
+            A(2 * i + 1, j) = -A_(i, j);
+        }
+        b[2 * i] = b_[i];
+        b[2 * i + 1] = -b_[i];
+    }
+    return std::make_unique<Symmetrical>(A, b, c, /*maximize=*/!minimize_);
 }

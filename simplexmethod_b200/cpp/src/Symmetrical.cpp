@@ -1,5 +1,5 @@
 // Symmetrical.cpp — symmetric-form container and its conversion to canonical
-// form (behaviour of reference src/ProblemTypes/Symmetrical.cpp:119-223).
+// form (behaviour of reference src/ProblemTypes/Symmetrical.cpp:119-273).
 #include "ProblemTypes/Symmetrical.h"
 
 #include <iostream>
@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "ProblemTypes/Canonical.h"
+#include "ProblemTypes/Common.h"
 
 Symmetrical::Symmetrical(const Eigen::MatrixXd& A, const Eigen::VectorXd& b, const Eigen::VectorXd& c, bool maximize)
     : A_(A), b_(b), c_(c), maximize_(maximize)
@@ -59,4 +60,12 @@ std::unique_ptr<Canonical> Symmetrical::ToCanonical() const
     auto out = std::make_unique<Canonical>(Ac, b_, cc, basis, /*minimize=*/!maximize_);
     out->SetOriginalVariablesCount(static_cast<int>(n));
     return out;
+}
+
+std::unique_ptr<Common> Symmetrical::ToCommon() const
+{
+    const auto rowType = maximize_ ? Common::ConstraintType::LessOrEqual : Common::ConstraintType::GreaterOrEqual;
+    return std::make_unique<Common>(A_, b_, c_, std::vector<Common::ConstraintType>(static_cast<size_t>(A_.rows()), rowType),
+                                    std::vector<Common::VariableType>(static_cast<size_t>(A_.cols()), Common::VariableType::NonNegative),
+                                    maximize_);
 }

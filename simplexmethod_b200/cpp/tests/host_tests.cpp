@@ -1,6 +1,7 @@
 // host_tests.cpp — CPU-only checks of the host types, restating what the
 // reference's gtest suite pins for them (reference: tests/test_canonical.cpp:
-// 31-39,68-76; tests/test_symmetrical.cpp:27-97; tests/test_parser.cpp:4-81).
+// 31-39,68-76; tests/test_symmetrical.cpp:27-97; tests/test_parser.cpp:4-81;
+// tests/test_common.cpp:39-94; tests/test_transformations.cpp:6-61).
 // Exit code 0 = all passed.  Needs no GPU (no numerical method is called).
 #include <cstdio>
 #include <cstdlib>
@@ -8,6 +9,7 @@
 
 #include "EnumerationSolver.h"
 #include "ProblemTypes/Canonical.h"
+#include "ProblemTypes/Common.h"
 #include "ProblemTypes/Symmetrical.h"
 #include "SymmetricalParser.h"
 
@@ -20,6 +22,14 @@ static Eigen::MatrixXd mat(int r, int c, std::initializer_list<double> rowmajor)
     int k = 0;
     for (double v : rowmajor) { m(k / c, k % c) = v; ++k; }
     return m;
+}
+
+static Eigen::VectorXd vec(std::initializer_list<double> il)
+{
+    Eigen::VectorXd v(static_cast<Eigen::Index>(il.size()));
+    Eigen::Index k = 0;
+    for (double x : il) v[k++] = x;
+    return v;
 }
 
 int main()
@@ -72,6 +82,77 @@ int main()
     CHECK(!dual->IsMaximization() && dual->GetConstraintsMatrix()(0, 1) == 3.0);
     CHECK(dual->GetRightHandSide()[1] == 8.0 && dual->GetObjectiveCoefficients()[0] == 5.0);
     CHECK(throws<std::invalid_argument>([&] { Symmetrical bad(As, cs, c, true); }));
+
+    // --- Common (tests/test_common.cpp:39-94): fixture A=[1 2;3 4], b=(5,6), c=(7,8), rows (<=, >=), x >= 0, max
+    using CT = Common::ConstraintType;
+    using VT = Common::VariableType;
+    {
+        Common com(As, bs, cs, {CT::LessOrEqual, CT::GreaterOrEqual}, {VT::NonNegative, VT::NonNegative}, true);
+        CHECK(com.IsMaximization() && com.GetConstraintsMatrix().rows() == 2 && com.GetConstraintsMatrix().cols() == 2);
+        CHECK(com.GetRightHandSide().size() == 2 && com.GetObjectiveCoefficients().size() == 2);
+        Eigen::VectorXd x12(2); x12[0] = 1; x12[1] = 2;
+        CHECK(com.Evaluate(x12) == 23.0);
+        CHECK(throws<std::invalid_argument>([&] { com.Evaluate(c); }));
+        Eigen::VectorXd b3(3);
+        CHECK(throws<std::invalid_argument>([&] { Common bad(As, b3, cs, {CT::LessOrEqual, CT::GreaterOrEqual}, {VT::NonNegative, VT::NonNegative}, true); }));
+        CHECK(throws<std::invalid_argument>([&] { Common bad(As, bs, cs, {CT::LessOrEqual}, {VT::NonNegative, VT::NonNegative}, true); }));
+        CHECK(throws<std::invalid_argument>([&] { Common bad(As, bs, cs, {CT::LessOrEqual, CT::Equal}, {VT::Free}, true); }));
+        Common com2(com);
+        CHECK(com2.IsMaximization() && com2.GetConstraintsMatrix().rows() == 2);
+        auto dcom = com.GetDual();                       // max -> min; <= row -> y >= 0, >= row -> y <= 0; x >= 0 -> >= rows
+        CHECK(dcom && !dcom->IsMaximization() && dcom->GetConstraintsMatrix().rows() == 2 && dcom->GetConstraintsMatrix().cols() == 2);
+        CHECK(dcom->GetConstraintsMatrix()(0, 1) == 3.0 && dcom->GetRightHandSide()[0] == 7.0 && dcom->GetObjectiveCoefficients()[1] == 6.0);
+        CHECK(dcom->GetVariableTypes()[0] == VT::NonNegative && dcom->GetVariableTypes()[1] == VT::NonPositive);
+        CHECK(dcom->GetConstraintTypes()[0] == CT::GreaterOrEqual && dcom->GetConstraintTypes()[1] == CT::GreaterOrEqual);
+        auto ddcom = dcom->GetDual();                    // the dual of the dual is the primal, types included
+        CHECK(ddcom->IsMaximization() && ddcom->GetConstraintsMatrix() == As && ddcom->GetRightHandSide() == bs);
+        CHECK(ddcom->GetConstraintTypes() == com.GetConstraintTypes() && ddcom->GetVariableTypes() == com.GetVariableTypes());
+        // symmetric form of the fixture: the >= row is negated
+        auto s1 = com.ToSymmetrical();
+        CHECK(s1->IsMaximization() && s1->GetConstraintsMatrix().rows() == 2 && s1->GetConstraintsMatrix()(1, 0) == -3.0 && s1->GetRightHandSide()[1] == -6.0);
+    }
+    {   // every row and variable kind at once, minimisation (Common.cpp:169-348)
+        Common gen(mat(3, 3, {1, 2, 3, 4, 5, 6, 7, 8, 9}), vec({10, 11, 12}), vec({1, -2, 3}),
+                   {CT::LessOrEqual, CT::GreaterOrEqual, CT::Equal}, {VT::Free, VT::NonNegative, VT::NonPositive}, false);
+        auto s2 = gen.ToSymmetrical();
+        CHECK(s2->IsMaximization());                     // always max / <=; min costs are negated
+        const Eigen::MatrixXd want = mat(4, 4, { 1, -1,  2, -3,
+                                                -4,  4, -5,  6,
+                                                 7, -7,  8, -9,
+                                                -7,  7, -8,  9});
+        CHECK(s2->GetConstraintsMatrix() == want);
+        CHECK(s2->GetRightHandSide() == vec({10, -11, 12, -12}));
+        CHECK(s2->GetObjectiveCoefficients() == vec({-1, 1, 2, 3}));
+        auto c2 = gen.ToCanonical();                     // = ToSymmetrical()->ToCanonical(): [A | I], slack basis, 4 original variables
+        CHECK(c2->GetConstraintsMatrix().rows() == 4 && c2->GetConstraintsMatrix().cols() == 8 && c2->IsMaximization());
+        CHECK(c2->GetOriginalVariablesCount() == 4 && c2->GetBasisIndices()[3] == 7 && c2->GetConstraintsMatrix()(3, 7) == 1.0);
+        auto dg = gen.GetDual();                         // min -> max: <= row -> y <= 0, >= row -> y >= 0, = row -> free
+        CHECK(dg->IsMaximization() && dg->GetVariableTypes() == (std::vector<VT>{VT::NonPositive, VT::NonNegative, VT::Free}));
+        CHECK(dg->GetConstraintTypes() == (std::vector<CT>{CT::Equal, CT::LessOrEqual, CT::GreaterOrEqual}));
+    }
+    {   // tests/test_transformations.cpp:6-40 Common -> Symmetrical -> Canonical, :42-61 dual of the dual
+        Common com(As, bs, cs, {CT::LessOrEqual, CT::LessOrEqual}, {VT::NonNegative, VT::NonNegative}, true);
+        auto sym = com.ToSymmetrical();
+        CHECK(sym && sym->GetConstraintsMatrix() == As && sym->GetRightHandSide() == bs && sym->GetObjectiveCoefficients() == cs);
+        auto can2 = sym->ToCanonical();
+        CHECK(can2 && can2->GetConstraintsMatrix().rows() == 2);
+        auto dd = smax.GetDual()->GetDual();
+        CHECK(dd->IsMaximization() && dd->GetConstraintsMatrix() == As && dd->GetRightHandSide() == bs && dd->GetObjectiveCoefficients() == cs);
+    }
+    {   // tests/test_symmetrical.cpp:87-97 ToCommon; tests/test_canonical.cpp:78-89 ToCommon; Canonical.cpp:230-303 ToSymmetrical
+        auto com = smax.ToCommon();
+        CHECK(com && com->IsMaximization() && com->GetConstraintTypes().size() == 2 && com->GetVariableTypes().size() == 2);
+        CHECK(com->GetConstraintTypes()[0] == CT::LessOrEqual && com->GetVariableTypes()[1] == VT::NonNegative);
+        CHECK(smin.ToCommon()->GetConstraintTypes()[1] == CT::GreaterOrEqual && !smin.ToCommon()->IsMaximization());
+        Canonical can2(can);
+        can2.SetOriginalVariablesCount(2);
+        auto cc = can2.ToCommon();
+        CHECK(cc && cc->GetObjectiveCoefficients().size() == 2 && cc->GetConstraintsMatrix().cols() == 2 && !cc->IsMaximization());
+        CHECK(cc->GetConstraintTypes()[0] == CT::Equal && cc->GetConstraintsMatrix()(1, 1) == 4.0 && cc->GetRightHandSide()[1] == 6.0);
+        auto cs2 = can2.ToSymmetrical();
+        CHECK(!cs2->IsMaximization() && cs2->GetConstraintsMatrix() == mat(4, 2, {1, 2, -1, -2, 3, 4, -3, -4}));
+        CHECK(cs2->GetRightHandSide() == vec({5, -5, 6, -6}) && cs2->GetObjectiveCoefficients() == cs);
+    }
 
     // --- parser (tests/test_parser.cpp)
     SymmetricalParser parser;
