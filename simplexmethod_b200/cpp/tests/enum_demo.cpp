@@ -65,7 +65,11 @@ int demo_main_cpp()
     print_vec("initial_x", x0);
     std::printf("initial_z %.17g\ninitial_basis_feasible %d\n", canonical->Evaluate(x0), canonical->IsFeasibleBasis() ? 1 : 0);
     solve_and_print("primal", *canonical);
-    solve_and_print("dual", *dual->ToCanonical());      // min b'y, A'y >= c: surplus + artificial columns
+    // The dual is solved from the general form: Common::ToSymmetrical turns "min b'y, A'y >= c" into
+    // "max -b'y, -A'y <= -c", whose canonical form has slacks only.  (Symmetrical::ToCanonical of a min
+    // problem adds zero-cost artificial columns, reference Symmetrical.cpp:191-222; enumerating THAT is a
+    // relaxation whose optimum is 0 — the reference leaves Big-M to its simplex solver.)
+    solve_and_print("dual", *common.GetDual()->ToCanonical());
     return 0;
 }
 

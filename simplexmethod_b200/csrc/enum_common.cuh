@@ -92,15 +92,15 @@ __device__ __forceinline__ double fnma(double a, double b, double c) { return __
 // ---------------------------------------------------------------------------
 // Warp + block reduction of (key, rank) by lexicographic min and of counters
 // by sum.  Result valid in thread 0 of the block.
-template <int kThreads>
+template <int kThreads, class Count>     // Count: uint32_t or uint64_t per-thread counters
 __device__ __forceinline__ void block_reduce(double& key, uint64_t& rank,
-                                             uint32_t& ns, uint32_t& ni, uint32_t& nf,
+                                             Count& ns, Count& ni, Count& nf,
                                              BlockPartial* out_slot, int n_warps = kThreads / 32)
 {
     constexpr int kWarps = kThreads / 32;   // capacity; n_warps <= kWarps are live
     __shared__ double   s_key[kWarps];
     __shared__ uint64_t s_rank[kWarps];
-    __shared__ uint32_t s_cnt[kWarps][3];
+    __shared__ uint64_t s_cnt[kWarps][3];
     const unsigned full = 0xffffffffu;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
