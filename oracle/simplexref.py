@@ -15,6 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "libsimplexref.so")
+DROPIN = os.path.join(_HERE, "_ref", "dropin_demo")     # INTEGRATION.md's drop-in built with the reference's own types
 REFERENCE = os.environ.get("SIMPLEX_REFERENCE", "/root/reference")
 COMMON, SYMMETRICAL, CANONICAL = 0, 1, 2
 TO_SYMMETRICAL, TO_CANONICAL, TO_COMMON, GET_DUAL = 0, 1, 2, 3
@@ -38,6 +39,8 @@ def build():
     """(Re)build from the reference's sources when they are present; otherwise keep what is there."""
     if os.path.isdir(os.path.join(REFERENCE, "src")):
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref", f"REF={REFERENCE}"])
+        if os.path.exists(os.path.join(os.path.dirname(_HERE), "simplexmethod_b200", "libenumgpu.so")):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "dropin", f"REF={REFERENCE}"])
     return SO if os.path.exists(SO) else None
 
 

@@ -239,3 +239,28 @@ def test_gpu_vs_reference_simplex_headline(gpu_lib):
     s = sm.EnumerationSolver(sm.Canonical(A, b, c, list(range(12)), minimize=not mx))
     x_gpu = s.solve()
     assert close(R.simplex_solve(A, b, c, list(range(12)), minimize=not mx), x_gpu)
+
+
+@pytest.mark.gpu
+def test_dropin_with_the_reference_types(gpu_lib, tmp_path):
+    """INTEGRATION.md §1 for real (oracle/dropin_demo.cpp): our EnumerationSolver.h in place of the reference's
+    stub, compiled with the reference's own Canonical / Symmetrical / parser / Solver; the reference user's flow
+    ParseFromFile -> ToCanonical -> Solver.solve() and EnumerationSolver.solve() gives the same vertex."""
+    import subprocess
+    assert os.path.exists(R.DROPIN), "oracle/_ref/dropin_demo was not built (make -C oracle dropin)"
+    rng = np.random.default_rng(5)
+    A = rng.integers(1, 10, size=(6, 10))
+    text = "maximize\nobjective:\n" + " ".join(str(v) for v in rng.integers(1, 10, size=10)) + "\nconstraints:\n" + \
+           "\n".join(" ".join(str(v) for v in row) + f" {int(rng.integers(20, 60))}" for row in A) + "\n"
+    big = tmp_path / "sym_6_10.txt"
+    big.write_text(text)
+    for path, want in ((os.path.join(ROOT, "tests", "golden", "lab_lp_symmetric.txt"), [5.0, 0.0, 0.0]), (str(big), None)):
+        out = subprocess.run([R.DROPIN, path], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        facts = {l.split()[0]: [float(v) for v in l.split()[1:]] for l in out.stdout.splitlines()}
+        assert close(facts["simplex_x"], facts["enumeration_x"])
+        if want:
+            assert facts["enumeration_x"] == want and facts["objective"] == [35.0]
+        else:
+            sym = SymmetricalParser().ParseFromString(text)
+            assert close(sym.Evaluate(facts["enumeration_x"]), facts["objective"][0]) and facts["counts"][0] == 8008
