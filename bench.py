@@ -190,9 +190,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION (and above): stdout carries the one JSON line only
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its debug output — at NCCL_DEBUG=WARN/VERSION that is the "NCCL version ..." banner — to stdout
+        # unless told otherwise: stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     algo = {"auto": _abi.ALGO_AUTO, "independent": _abi.ALGO_INDEPENDENT, "shared": _abi.ALGO_SHARED}[args.algo]
 
