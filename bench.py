@@ -331,16 +331,14 @@ def main():
         fpb = 2 * 39.06 + 8.75 + 0.00           # DFMA x2 + DMUL + DADD thread-instructions per basis
         ex = shard * fpb / (kern_ms_own * 1e-3) / 1e12
         executed = {"flops_per_basis": fpb, "tflops": ex, "frac_of_peak": ex / probe if probe > 0 else None,
-                    "warp_instructions_per_basis": 6.85, "fp64_pipe_busy_pct": 30.2, "issue_slots_busy_pct": 59.9,
+                    "warp_instructions_per_basis": 6.80, "fp64_pipe_busy_pct": 30.4, "issue_slots_busy_pct": 59.9,
                     "source": "profiles/r1_k_shared_m12n40_ncu_key_metrics.csv (ncu --set full, full-range launch)"}
     roofline = {"bound": "fp64", "achieved": achieved, "peak": probe, "unit": "TFLOP/s",
                 "frac": achieved / probe if probe > 0 else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one k_shared<12> launch over the full
                 # C(40,12) range, from the ncu --set full capture under profiles/ (r1_k_shared_m12n40_ncu_key_metrics.csv)
-                "traffic": 69286400 if (m, n, world) == (12, 40, 1) and res.algo_used == _abi.ALGO_SHARED else None,
-                "traffic_unit": "bytes per launch under ncu's cold caches (algorithmic input: 13 KB; the rest is the write-back and "
-                                "re-fetch of ~0.06 spilled 4-byte words per basis plus instruction fetch and tables: "
-                                "1.2 GB/s against 7.7 TB/s of HBM, the kernel is FP64/issue bound)",
+                "traffic": 811776 if (m, n, world) == (12, 40, 1) and res.algo_used == _abi.ALGO_SHARED else None,
+                "traffic_unit": "bytes per launch (algorithmic input: 13 KB; the rest is instruction fetch, tables, spill write-back)",
                 "peak_source": "in-run register-resident DFMA-chain probe (enumgpu_fp64_peak_tflops); "
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
