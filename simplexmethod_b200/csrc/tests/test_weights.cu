@@ -4,10 +4,16 @@
 //   * child intervals are contiguous and in lexicographic order;
 //   * weight_unrank inverts weight_of_child anywhere inside an interval and
 //     reports the interval's header;
-//   * the total equals the sum of the level-0 subtrees.
+//   * the total equals the sum of the level-0 subtrees;
+//   * tail_group_start (the closed form a window uses to step back to the first child of a tail group) agrees
+//     with weight_of_child / weight_unrank;
+//   * handout_window: the hand-outs of all shards of a launch tile [w_lo, w_hi) exactly once, whole units first
+//     and the last round in kFineSplit pieces.
 // Exit code 0 = all passed.  Needs no GPU.
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
+#include <utility>
 #include <vector>
 
 #include "../k_shared.cuh"
@@ -53,6 +59,18 @@ static int run(int n, int m)
             CHECK(off == pr);
             CHECK(h == hdr);
         }
+        {   // stepping back from this child to the first child of its tail group
+            const int t0 = (S[P - 2] + 1 > n - kTailR) ? S[P - 2] + 1 : n - kTailR;
+            if (S[P - 1] > t0) {
+                uint64_t wg = w; uint32_t hg = 12345;
+                tail_group_start(C, n, m, [&](int i) { return S[i]; }, &wg, &hg);
+                std::vector<int> G(S);
+                G[P - 1] = t0;
+                CHECK(wg == weight_of_child(C, n, m, G.data()));
+                weight_unrank(C, n, m, wg, T.data(), &off, &h);
+                CHECK(off == 0 && h == hg && T[P - 1] == t0);
+            }
+        }
         expect += hdr + wchild + leaves;
         ++n_children; bases += leaves;
         int i = P - 1;                                         // next valid prefix
@@ -69,8 +87,40 @@ static int run(int n, int m)
     return 0;
 }
 
+// every hand-out of every shard, sorted: the windows must tile [w_lo, w_hi)
+static int run_handouts(uint64_t w_lo, uint64_t span, uint64_t G, uint32_t shards, uint64_t warps)
+{
+    const int n = (int)shards, m = (int)warps;        // for CHECK's message
+    std::vector<std::pair<uint64_t, uint64_t>> wins;
+    const uint64_t nu_all = (span + G - 1) / G;
+    uint64_t whole = 0, pieces = 0;
+    for (uint32_t sh = 0; sh < shards; ++sh) {
+        HandoutPlan hp{};
+        hp.unit_weight = G; hp.w_lo = w_lo; hp.w_hi = w_lo + span;
+        CHECK(plan_handouts(nu_all, sh, shards, warps, &hp));
+        CHECK(hp.n_units >= hp.n_coarse_first && hp.n_handouts == hp.n_coarse_first + (hp.n_units - hp.n_coarse_first) * kFineSplit);
+        for (uint64_t k = 0; k < hp.n_handouts; ++k) {
+            uint64_t a, b;
+            if (!handout_window(hp, k, &a, &b)) continue;
+            CHECK(a < b && b - a <= G);
+            (k < hp.n_coarse_first ? whole : pieces) += 1;
+            wins.emplace_back(a, b);
+        }
+    }
+    std::sort(wins.begin(), wins.end());
+    uint64_t at = w_lo;
+    for (auto& w : wins) { CHECK(w.first == at); at = w.second; }
+    CHECK(at == w_lo + span);
+    CHECK(nu_all < 2 * shards || pieces > 0);          // there is a fine tail whenever a shard has 2+ units
+    return 0;
+}
+
 int main()
 {
+    const uint64_t hcases[][5] = {{0, 1000000, 1024, 1, 16}, {77, 123457, 1024, 8, 4}, {5, 4096, 1024, 3, 64}, {0, 1023, 1024, 2, 8},
+                                  {0, 5611770000ull, 21404, 8, 2368}, {1000, 5611770000ull, 21404, 1, 2368}, {0, 99999, 1028, 5, 7}};
+    for (auto& h : hcases)
+        if (run_handouts(h[0], h[1], h[2] - h[2] % kFineSplit, (uint32_t)h[3], h[4])) return 1;
     const int cases[][2] = {{6, 6}, {9, 6}, {12, 7}, {13, 8}, {16, 9}, {15, 10}, {18, 12}, {20, 16}, {24, 8}, {22, 9}};
     for (auto& c : cases)
         if (run(c[0], c[1])) return 1;
