@@ -190,8 +190,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL writes its debug output — at NCCL_DEBUG=WARN/VERSION that is the "NCCL version ..." banner — to stdout
-        # unless told otherwise: stdout carries the one JSON line only
+        # stdout carries the one JSON line only.  At NCCL_DEBUG=VERSION (this pool's default) NCCL prints its
+        # "NCCL version ..." banner on stdout and ignores NCCL_DEBUG_FILE (honoured from WARN up): raise VERSION to
+        # WARN and send NCCL's debug output to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     algo = {"auto": _abi.ALGO_AUTO, "independent": _abi.ALGO_INDEPENDENT, "shared": _abi.ALGO_SHARED}[args.algo]
