@@ -9,6 +9,7 @@
 // Entry points (plain pointers and sizes; matrices column-major, lda = rows):
 //   ref_convert          Common / Symmetrical / Canonical -> ToSymmetrical / ToCanonical / ToCommon / GetDual
 //   ref_parse            SymmetricalParser::ParseFromString
+//   ref_print            Print() of any of the three forms, captured from std::cout
 //   ref_basic_solution   Canonical::GetBasicSolution + IsFeasibleBasis + Evaluate for one designated basis
 //   ref_enumerate        the enumeration path AS THE REFERENCE WOULD RUN IT: the class
 //                        EnumerationSolver is an empty stub (src/EnumerationSolver.h:3-10), so the loop over
@@ -21,7 +22,9 @@
 #include <cstdint>
 #include <cstring>
 #include <exception>
+#include <iostream>
 #include <memory>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -134,6 +137,41 @@ int ref_convert(const ref_problem* in, int32_t op, ref_problem* out)
         g_err = e.what();
         return -3;
     }
+}
+
+// the text the reference's Print() writes to std::cout for this problem; returns its length (or -3 / -2: too long)
+int ref_print(const ref_problem* in, char* buf, int32_t cap)
+{
+    g_err.clear();
+    std::ostringstream text;
+    std::streambuf* old = std::cout.rdbuf(text.rdbuf());
+    int rc = 0;
+    try {
+        const Eigen::MatrixXd A = mat(in->m, in->n, in->A);
+        const Eigen::VectorXd b = vec(in->m, in->b), c = vec(in->n, in->c);
+        if (in->kind == REF_COMMON) {
+            std::vector<Common::ConstraintType> rt;
+            std::vector<Common::VariableType> vt;
+            for (int i = 0; i < in->m; ++i) rt.push_back((Common::ConstraintType)in->row_types[i]);
+            for (int j = 0; j < in->n; ++j) vt.push_back((Common::VariableType)in->var_types[j]);
+            Common(A, b, c, rt, vt, in->maximize != 0).Print();
+        } else if (in->kind == REF_SYMMETRICAL) {
+            Symmetrical(A, b, c, in->maximize != 0).Print();
+        } else {
+            Canonical p(A, b, c, std::vector<int>(in->basis, in->basis + in->m), in->maximize == 0);
+            p.SetOriginalVariablesCount(in->n_orig);
+            p.Print();
+        }
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        rc = -3;
+    }
+    std::cout.rdbuf(old);
+    if (rc) return rc;
+    const std::string t = text.str();
+    if ((int)t.size() + 1 > cap) { g_err = "output capacity too small"; return -2; }
+    std::memcpy(buf, t.c_str(), t.size() + 1);
+    return (int)t.size();
 }
 
 // returns 0 and fills *out (kind = SYMMETRICAL), or 1 = the parser returned nullptr (message in ref_last_error)

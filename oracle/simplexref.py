@@ -57,6 +57,7 @@ def lib():
         L.ref_last_error.restype = C.c_char_p
         L.ref_convert.argtypes = [C.POINTER(Problem), C.c_int32, C.POINTER(Problem)]
         L.ref_parse.argtypes = [C.c_char_p, C.POINTER(Problem)]
+        L.ref_print.argtypes = [C.POINTER(Problem), C.c_char_p, C.c_int32]
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         L.ref_basic_solution.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, ip, C.c_int32, dp, ip, dp]
         L.ref_enumerate.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, C.c_int32, C.POINTER(C.c_uint8), C.POINTER(EnumResult)]
@@ -121,6 +122,17 @@ def convert(kind, op, A, b, c, maximize, **kw):
     if rc != 0:
         raise RuntimeError(last_error())
     return dst.take()
+
+
+def print_problem(kind, A, b, c, maximize, **kw) -> str:
+    """What the reference's Print() writes to std::cout for this problem."""
+    A = np.asarray(A, dtype=np.float64)
+    src = _Buf(*A.shape).fill(kind, A, b, c, maximize, **kw)
+    buf = C.create_string_buffer(1 << 16)
+    n = lib().ref_print(C.byref(src.s), buf, len(buf))
+    if n < 0:
+        raise RuntimeError(last_error())
+    return buf.raw[:n].decode("utf-8")
 
 
 def parse(text: str):

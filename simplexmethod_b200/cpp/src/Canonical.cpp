@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "PrintLP.h"
 #include "ProblemTypes/Common.h"
 #include "ProblemTypes/Symmetrical.h"
 #include "enumgpu.h"
@@ -32,8 +33,12 @@ double Canonical::Evaluate(const Eigen::VectorXd& solution) const
 
 void Canonical::Print() const
 {
-    std::cout << "Canonical LP: " << (minimize_ ? "min" : "max") << " c'x, Ax = b, x >= 0   (" << A_.rows() << " x "
-              << A_.cols() << ", " << n_orig_ << " original + " << (c_.size() - n_orig_) << " added variables)\n";
+    std::ostream& os = std::cout;
+    lp_print::objective(os, "=== Каноническая форма задачи ЛП ===", !minimize_, c_);
+    lp_print::rows(os, "При ограничениях (Ax = b):", A_, b_, "*", [](Eigen::Index) { return " = "; });
+    os << "\nВсе переменные неотрицательны: x_i >= 0\n\nБазисные переменные: ";
+    for (size_t i = 0; i < basis_.size(); ++i) os << (i ? ", " : "") << "x" << (basis_[i] + 1);
+    os << "\nКоличество исходных переменных: " << n_orig_ << "\nДополнительных переменных: " << (c_.size() - n_orig_) << "\n";
 }
 
 void Canonical::SetOriginalVariablesCount(int count)

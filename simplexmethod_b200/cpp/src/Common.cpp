@@ -6,6 +6,7 @@
 #include <iostream>
 #include <stdexcept>
 
+#include "PrintLP.h"
 #include "ProblemTypes/Canonical.h"
 #include "ProblemTypes/Symmetrical.h"
 
@@ -30,13 +31,13 @@ double Common::Evaluate(const Eigen::VectorXd& solution) const
 
 void Common::Print() const
 {
-    static const char* const rel[] = {"<=", ">=", "="};
-    static const char* const dom[] = {"free", ">= 0", "<= 0"};
-    std::cout << "General LP: " << (maximize_ ? "max" : "min") << " c'x   (" << A_.rows() << " x " << A_.cols() << ")\n  rows:";
-    for (auto t : rowTypes_) std::cout << ' ' << rel[static_cast<int>(t)];
-    std::cout << "\n  variables:";
-    for (auto t : varTypes_) std::cout << ' ' << dom[static_cast<int>(t)];
-    std::cout << '\n';
+    static const char* const rel[] = {"<=", ">=", "="};                    // no blanks, and no '*' in the rows: as the reference prints
+    static const char* const dom[] = {"∈R", " >= 0", " <= 0"};
+    std::ostream& os = std::cout;
+    lp_print::objective(os, "=== Общая форма задачи ЛП ===", maximize_, c_);
+    lp_print::rows(os, "При ограничениях:", A_, b_, "", [this](Eigen::Index i) { return rel[static_cast<int>(rowTypes_[static_cast<size_t>(i)])]; });
+    os << "\nОграничения на переменные:\n";
+    for (size_t j = 0; j < varTypes_.size(); ++j) os << "x" << (j + 1) << ": " << dom[static_cast<int>(varTypes_[j])] << "\n";
 }
 
 std::unique_ptr<Symmetrical> Common::ToSymmetrical() const

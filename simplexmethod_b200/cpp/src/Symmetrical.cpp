@@ -6,6 +6,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "PrintLP.h"
 #include "ProblemTypes/Canonical.h"
 #include "ProblemTypes/Common.h"
 
@@ -24,8 +25,11 @@ double Symmetrical::Evaluate(const Eigen::VectorXd& solution) const
 
 void Symmetrical::Print() const
 {
-    std::cout << "Symmetrical LP: " << (maximize_ ? "max c'x, Ax <= b" : "min c'x, Ax >= b") << ", x >= 0   (" << A_.rows()
-              << " x " << A_.cols() << ")\n";
+    std::ostream& os = std::cout;
+    lp_print::objective(os, "=== Симметричная форма задачи ЛП ===", maximize_, c_);
+    const char* rel = maximize_ ? " <= " : " >= ";
+    lp_print::rows(os, "При ограничениях:", A_, b_, "*", [rel](Eigen::Index) { return rel; });
+    os << "\nВсе переменные неотрицательны: x_i >= 0\n";
 }
 
 std::unique_ptr<Symmetrical> Symmetrical::GetDual() const

@@ -5,7 +5,9 @@
 // Exit code 0 = all passed.  Needs no GPU (no numerical method is called).
 #include <cstdio>
 #include <cstdlib>
+#include <iostream>
 #include <stdexcept>
+#include <string>
 
 #include "EnumerationSolver.h"
 #include "ProblemTypes/Canonical.h"
@@ -32,8 +34,28 @@ static Eigen::VectorXd vec(std::initializer_list<double> il)
     return v;
 }
 
-int main()
+// the three Print() layouts on a fixture with negative, zero and fractional coefficients (compared with the
+// reference's own output by tests/test_reference_code.py)
+static void print_fixture()
 {
+    using CT = Common::ConstraintType;
+    using VT = Common::VariableType;
+    const Eigen::MatrixXd A = mat(3, 3, {1, -2, 0.5, 0, 4, -6, 7, 8.25, 9});
+    const Eigen::VectorXd b = vec({10, -11, 1e-7}), c = vec({1, -2, 0});
+    Common(A, b, c, {CT::LessOrEqual, CT::GreaterOrEqual, CT::Equal}, {VT::Free, VT::NonNegative, VT::NonPositive}, false).Print();
+    std::cout << "---\n";
+    Symmetrical(A, b, c, true).Print();
+    std::cout << "---\n";
+    Symmetrical(A, b, c, false).Print();
+    std::cout << "---\n";
+    Canonical can(mat(2, 4, {1, -2, 1, 0, 3, 4.5, 0, 1}), vec({5, 6}), vec({7, -8, 0, 0}), {2, 3}, false);
+    can.SetOriginalVariablesCount(2);
+    can.Print();
+}
+
+int main(int argc, char** argv)
+{
+    if (argc > 1 && std::string(argv[1]) == "--print") { print_fixture(); return 0; }
     // --- Canonical: fixture of tests/test_canonical.cpp:12-22
     const Eigen::MatrixXd A = mat(2, 4, {1, 2, 1, 0, 3, 4, 0, 1});
     Eigen::VectorXd b(2); b[0] = 5; b[1] = 6;

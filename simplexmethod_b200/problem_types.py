@@ -35,7 +35,26 @@ def _checked(A, b, c):
     return np.asfortranarray(A), np.ascontiguousarray(b), np.ascontiguousarray(c)
 
 
+def _terms(values, sep: str) -> str:
+    """"c1*x1 + c2*x2-c3*x3": " + " only in front of a non-negative coefficient; numbers as operator<<(double) prints them."""
+    out = []
+    for j, v in enumerate(values):
+        out.append((" + " if j > 0 and v >= 0 else "") + f"{v:g}{sep}x{j + 1}")
+    return "".join(out)
+
+
+def _lp_text(title, maximize, A, b, c, heading, sep, rel) -> str:
+    """Header, objective and rows in the layout of the reference's Print() methods (Common.cpp:86-137,
+    Symmetrical.cpp:70-97, Canonical.cpp:88-123); rel(i) is the text between row i and its right-hand side."""
+    lines = [title, ("Максимизировать: " if maximize else "Минимизировать: ") + _terms(c, "*"), "", heading]
+    lines += [_terms(A[i], sep) + rel(i) + f"{b[i]:g}" for i in range(A.shape[0])]
+    return "\n".join(lines) + "\n"
+
+
 class _Problem:
+    def Print(self):
+        print(self.PrintText(), end="")
+
     def GetConstraintsMatrix(self): return self._A
     def GetRightHandSide(self): return self._b
     def GetObjectiveCoefficients(self): return self._c
@@ -54,6 +73,11 @@ class Symmetrical(_Problem):
     def __init__(self, A, b, c, maximize: bool):
         self._A, self._b, self._c = _checked(A, b, c)      # Symmetrical.cpp:17-29
         self._maximize = bool(maximize)
+
+    def PrintText(self) -> str:
+        rel = " <= " if self._maximize else " >= "
+        return _lp_text("=== Симметричная форма задачи ЛП ===", self._maximize, self._A, self._b, self._c,
+                        "При ограничениях:", "*", lambda i: rel) + "\nВсе переменные неотрицательны: x_i >= 0\n"
 
     def GetDual(self) -> "Symmetrical":
         """Transpose A, swap b and c, flip the sense (Symmetrical.cpp:119-140)."""
@@ -110,6 +134,13 @@ class Common(_Problem):
         self._rows = [ConstraintType(t) for t in constraintTypes]
         self._vars = [VariableType(t) for t in variableTypes]
         self._maximize = bool(maximize)
+
+    def PrintText(self) -> str:
+        rel = {ConstraintType.LessOrEqual: "<=", ConstraintType.GreaterOrEqual: ">=", ConstraintType.Equal: "="}
+        dom = {VariableType.Free: "∈R", VariableType.NonNegative: " >= 0", VariableType.NonPositive: " <= 0"}
+        return _lp_text("=== Общая форма задачи ЛП ===", self._maximize, self._A, self._b, self._c,
+                        "При ограничениях:", "", lambda i: rel[self._rows[i]]) + "\nОграничения на переменные:\n" + \
+            "".join(f"x{j + 1}: {dom[t]}\n" for j, t in enumerate(self._vars))
 
     def GetConstraintTypes(self) -> List[ConstraintType]: return self._rows
     def GetVariableTypes(self) -> List[VariableType]: return self._vars
@@ -173,6 +204,16 @@ def _canonical_to_symmetrical(self: Canonical) -> Symmetrical:
     return Symmetrical(A, b, self._c[:n], not self._minimize)
 
 
+def _canonical_print_text(self: Canonical) -> str:
+    n = self._c.size
+    return _lp_text("=== Каноническая форма задачи ЛП ===", not self._minimize, self._A, self._b, self._c,
+                    "При ограничениях (Ax = b):", "*", lambda i: " = ") + \
+        "\nВсе переменные неотрицательны: x_i >= 0\n\nБазисные переменные: " + ", ".join(f"x{j + 1}" for j in self._basis) + \
+        f"\nКоличество исходных переменных: {self._n_orig}\nДополнительных переменных: {n - self._n_orig}\n"
+
+
+Canonical.PrintText = _canonical_print_text
+Canonical.Print = _Problem.Print
 Canonical.ToCommon = _canonical_to_common
 Canonical.ToSymmetrical = _canonical_to_symmetrical
 

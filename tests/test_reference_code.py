@@ -111,6 +111,29 @@ def test_parser_equals_the_reference(k):
         same_problem(ref, mine)
 
 
+def test_print_layouts_equal_the_reference():
+    """IProblem::Print() of the three forms: the Python mirror and the C++ host types (cpp/tests/host_tests --print)
+    write the reference's text character for character (Common.cpp:86-137, Symmetrical.cpp:70-97, Canonical.cpp:88-123)."""
+    import subprocess
+    A = np.array([[1, -2, 0.5], [0, 4, -6], [7, 8.25, 9]])
+    b, c = np.array([10, -11, 1e-7]), np.array([1.0, -2.0, 0.0])
+    rt, vt = [0, 1, 2], [0, 1, 2]
+    Ac, bc, cc = np.array([[1, -2, 1, 0], [3, 4.5, 0, 1]]), np.array([5.0, 6.0]), np.array([7.0, -8.0, 0.0, 0.0])
+    can = sm.Canonical(Ac, bc, cc, [2, 3], minimize=False)
+    can.SetOriginalVariablesCount(2)
+    want = [R.print_problem(R.COMMON, A, b, c, False, row_types=rt, var_types=vt),
+            R.print_problem(R.SYMMETRICAL, A, b, c, True), R.print_problem(R.SYMMETRICAL, A, b, c, False),
+            R.print_problem(R.CANONICAL, Ac, bc, cc, True, basis=[2, 3], n_orig=2)]
+    mine = [Common(A, b, c, [CT(t) for t in rt], [VT(t) for t in vt], False).PrintText(),
+            Symmetrical(A, b, c, True).PrintText(), Symmetrical(A, b, c, False).PrintText(), can.PrintText()]
+    assert mine == want
+    assert "1*x1-2*x2 + 0*x3" in want[0] and "0x1 + 4x2-6x3>=-11" in want[0] and "x1: ∈R" in want[0]      # what the layout looks like
+    cpp = os.path.join(ROOT, "simplexmethod_b200", "cpp")
+    subprocess.check_call(["make", "-C", cpp, "-s"])
+    out = subprocess.run([os.path.join(cpp, "build", "host_tests"), "--print"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split("---\n") == want
+
+
 # ---- per basis: the reference's QR-based primitives vs the oracle's frozen GE --------------------
 
 @pytest.mark.parametrize("name", sorted(TINY))
