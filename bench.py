@@ -366,16 +366,16 @@ def main():
     # executed (not algorithmic) work of k_shared, from the ncu capture under profiles/
     executed = None
     if res.algo_used == _abi.ALGO_SHARED and (m, n) == (12, 40):
-        fpb = 2 * 39.06 + 8.75 + 0.00           # DFMA x2 + DMUL + DADD thread-instructions per basis
+        fpb = 2 * 39.27 + 8.79 + 0.00           # DFMA x2 + DMUL + DADD thread-instructions per basis
         ex = shard * fpb / (kern_ms_own * 1e-3) / 1e12
         executed = {"flops_per_basis": fpb, "tflops": ex, "frac_of_peak": ex / probe if probe > 0 else None,
-                    "warp_instructions_per_basis": 6.80, "fp64_pipe_busy_pct": 30.4, "issue_slots_busy_pct": 59.9,
+                    "warp_instructions_per_basis": 6.54, "fp64_pipe_busy_pct": 31.4, "issue_slots_busy_pct": 59.5,
                     "source": "profiles/r1_k_shared_m12n40_ncu_key_metrics.csv (ncu --set full, full-range launch)"}
     roofline = {"bound": "fp64", "achieved": achieved, "peak": probe, "unit": "TFLOP/s",
                 "frac": achieved / probe if probe > 0 else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one k_shared<12> launch over the full
                 # C(40,12) range, from the ncu --set full capture under profiles/ (r1_k_shared_m12n40_ncu_key_metrics.csv)
-                "traffic": 811776 if (m, n, world) == (12, 40, 1) and res.algo_used == _abi.ALGO_SHARED else None,
+                "traffic": 1389056 if (m, n, world) == (12, 40, 1) and res.algo_used == _abi.ALGO_SHARED else None,
                 "traffic_unit": "bytes per launch (algorithmic input: 13 KB; the rest is instruction fetch, tables, spill write-back)",
                 "peak_source": "in-run register-resident DFMA-chain probe (enumgpu_fp64_peak_tflops); "
                                "MEASURED_PEAKS.json has no FP64 figure",

@@ -60,8 +60,8 @@ try:
     ksrc = open(os.path.join(root, "simplexmethod_b200", "csrc", "k_shared.cuh")).read().split("\n")
     marks = []
     keys = (("__device__ __noinline__ void drain_fn", "drain_fn"), ("k_shared(const SharedParams sp", "prologue"),
-            ("------------- unit loop", "unit start (unrank, align)"), ("---- level Q from A", "level q from A"),
-            ("---- level Q+1 (parent)", "parent level"), ("---- children of this parent", "child level"),
+            ("------------- unit loop", "unit start (unrank, align)"), ("---- level QA from A", "level q-1 from A"),
+            ("---- level Q (depth-q node)", "level q (one step)"), ("---- level Q+1 (parent)", "parent level"), ("---- children of this parent", "child level"),
             ("--------- leaves ---", "item setup (a,b,c)"), ("---- the shared loop over the last column", "d loop"),
             ("---- next child of the same parent", "next child / parent"), ("--------- reduction", "reduction"), ("// host side", "host"))
     for i, l in enumerate(ksrc, 1):
