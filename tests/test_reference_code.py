@@ -193,6 +193,39 @@ def test_reference_enumeration_vs_oracle_dense(oracle, m, n, seed):
     _compare(ref, res, m)
 
 
+def small_degenerate_lp(seed, m=5, n=13):
+    """Small-integer LP with duplicated, scaled and summed columns (exactly singular bases), a right-hand side built
+    from a vertex with only m-2 positive components (degenerate vertices) and tied costs (exact ties at the optimum)."""
+    rng = np.random.default_rng(seed)
+    A = rng.integers(-3, 4, size=(m, n)).astype(float)
+    A[:, n - 1] = A[:, 0]; A[:, n - 2] = 2 * A[:, 1]; A[:, n - 3] = A[:, 2] + A[:, 3]
+    x0 = np.zeros(n)
+    x0[rng.choice(n - 3, size=m - 2, replace=False)] = rng.integers(1, 4, size=m - 2)
+    c = rng.integers(-4, 5, size=n).astype(float)
+    c[n - 1] = c[0]; c[n - 2] = 2 * c[1]
+    return np.asfortranarray(A), A @ x0, c, bool(seed % 2)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_degenerate_lps_classes_agree_ties_may_not(oracle, seed):
+    """Degenerate LPs: the class of every basis (hundreds of exactly singular ones) and all counters agree with the
+    reference's code.  The winner need not: tied vertices have objectives that differ in the last bits, differently
+    under Householder QR (reference) and partial-pivot GE (frozen arithmetic), so 'first strict improvement' lands on
+    different members of the tie — the north star asks for the identical basis on non-degenerate problems only.
+    Both winners are optimal to 1e-9; GPU and oracle share one arithmetic and agree exactly (test_gpu_parity)."""
+    A, b, c, mx = small_degenerate_lp(seed)
+    ref, st_ref = R.enumerate_bases(A, b, c, mx, want_status=True)
+    res, st = oracle.solve(A, b, c, mx, want_status=True)
+    assert np.array_equal(st_ref, st) and res.n_singular > 100
+    assert (ref.n_singular, ref.n_infeasible, ref.n_feasible) == (res.n_singular, res.n_infeasible, res.n_feasible)
+    assert ref.status == res.status
+    if res.status == 0:
+        assert close(ref.objective, res.objective)
+        # each side's winner, evaluated by the other side, is a tie
+        st_o, x_o, z_o = oracle.eval_basis(A, b, c, mx, list(ref.basis)[:A.shape[0]])
+        assert st_o == oracle.FEASIBLE and close(z_o, res.objective)
+
+
 def test_reference_enumeration_vs_oracle_headline_window(oracle):
     """m=12, n=40: 12 000 ranks around the optimum (rank 826 261 626) and a window of the densest region."""
     A, b, c, mx = lpgen.dense_lp(12, 40, 1)
