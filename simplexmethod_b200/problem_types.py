@@ -185,39 +185,6 @@ class Common(_Problem):
         return Common(self._A.T, self._c, self._b, dual_rows, dual_vars, not mx)
 
 
-def _canonical_to_common(self: Canonical) -> Common:
-    """Original variables only, rows as equalities (Canonical.cpp:199-228)."""
-    m, n = self._A.shape[0], self._n_orig
-    return Common(self._A[:, :n], self._b, self._c[:n], [ConstraintType.Equal] * m, [VariableType.NonNegative] * n,
-                  not self._minimize)
-
-
-def _canonical_to_symmetrical(self: Canonical) -> Symmetrical:
-    """Original variables only; each equality becomes (row, -row) (Canonical.cpp:230-303)."""
-    m, n = self._A.shape[0], self._n_orig
-    A = np.empty((2 * m, n))
-    A[0::2] = self._A[:, :n]
-    A[1::2] = -self._A[:, :n]
-    b = np.empty(2 * m)
-    b[0::2] = self._b
-    b[1::2] = -self._b
-    return Symmetrical(A, b, self._c[:n], not self._minimize)
-
-
-def _canonical_print_text(self: Canonical) -> str:
-    n = self._c.size
-    return _lp_text("=== Каноническая форма задачи ЛП ===", not self._minimize, self._A, self._b, self._c,
-                    "При ограничениях (Ax = b):", "*", lambda i: " = ") + \
-        "\nВсе переменные неотрицательны: x_i >= 0\n\nБазисные переменные: " + ", ".join(f"x{j + 1}" for j in self._basis) + \
-        f"\nКоличество исходных переменных: {self._n_orig}\nДополнительных переменных: {n - self._n_orig}\n"
-
-
-Canonical.PrintText = _canonical_print_text
-Canonical.Print = _Problem.Print
-Canonical.ToCommon = _canonical_to_common
-Canonical.ToSymmetrical = _canonical_to_symmetrical
-
-
 class SymmetricalParser:
     """Text format of the reference (SymmetricalParser.cpp:44-193): a sense line
     (maximize | max | minimize | min), ``objective:`` followed by coefficient rows,

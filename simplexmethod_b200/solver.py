@@ -83,6 +83,38 @@ class Canonical:
         dual.SetOriginalVariablesCount(2 * m)
         return dual
 
+    # -- back to the other forms, original variables only (Canonical.cpp:199-303) --
+    def ToCommon(self):
+        """Rows stay equalities, variables >= 0 (reference Canonical.cpp:199-228)."""
+        from .problem_types import Common, ConstraintType, VariableType
+        m, n = self._A.shape[0], self._n_orig
+        return Common(self._A[:, :n], self._b, self._c[:n], [ConstraintType.Equal] * m, [VariableType.NonNegative] * n,
+                      not self._minimize)
+
+    def ToSymmetrical(self):
+        """Each equality becomes the pair (row, -row) with the sense's inequality (reference Canonical.cpp:230-303)."""
+        from .problem_types import Symmetrical
+        m, n = self._A.shape[0], self._n_orig
+        A = np.empty((2 * m, n))
+        A[0::2] = self._A[:, :n]
+        A[1::2] = -self._A[:, :n]
+        b = np.empty(2 * m)
+        b[0::2] = self._b
+        b[1::2] = -self._b
+        return Symmetrical(A, b, self._c[:n], not self._minimize)
+
+    def PrintText(self) -> str:
+        """The text the reference's Canonical::Print() writes (Canonical.cpp:88-123)."""
+        from .problem_types import _lp_text
+        return _lp_text("=== Каноническая форма задачи ЛП ===", not self._minimize, self._A, self._b, self._c,
+                        "При ограничениях (Ax = b):", "*", lambda i: " = ") + \
+            "\nВсе переменные неотрицательны: x_i >= 0\n\nБазисные переменные: " + \
+            ", ".join(f"x{j + 1}" for j in self._basis) + \
+            f"\nКоличество исходных переменных: {self._n_orig}\nДополнительных переменных: {self._c.size - self._n_orig}\n"
+
+    def Print(self):
+        print(self.PrintText(), end="")
+
     # -- per-basis numerics: on the GPU, through enumgpu_eval_basis ---------
     def _eval_designated(self):
         ps = _problem_struct(self._A, self._b, self._c, not self._minimize)
