@@ -27,6 +27,8 @@ def test_reference_arm_json_cpu():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] > 1e5
     assert d["e2e"] == {"value": d["value"], "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+    rc = d["reference_code"]            # side figure: the reference's own per-basis code (oracle/_ref), when built
+    assert rc is None or rc.get("value", 0) > 1e3 or "unavailable" in rc
 
 
 @pytest.mark.gpu
