@@ -56,6 +56,20 @@ static void print_fixture()
 int main(int argc, char** argv)
 {
     if (argc > 1 && std::string(argv[1]) == "--print") { print_fixture(); return 0; }
+    if (argc > 2 && std::string(argv[1]) == "--parse") {        // one line per file: "null" or "maximize m n A(row-major) b c"
+        for (int k = 2; k < argc; ++k) {
+            SymmetricalParser fp;
+            auto sym = fp.ParseFromFile(argv[k]);
+            if (!sym) { std::puts("null"); continue; }
+            const Eigen::MatrixXd& M = sym->GetConstraintsMatrix();
+            std::printf("%d %d %d", sym->IsMaximization() ? 1 : 0, (int)M.rows(), (int)M.cols());
+            for (Eigen::Index i = 0; i < M.rows(); ++i) for (Eigen::Index j = 0; j < M.cols(); ++j) std::printf(" %.17g", M(i, j));
+            for (Eigen::Index i = 0; i < M.rows(); ++i) std::printf(" %.17g", sym->GetRightHandSide()[i]);
+            for (Eigen::Index j = 0; j < M.cols(); ++j) std::printf(" %.17g", sym->GetObjectiveCoefficients()[j]);
+            std::puts("");
+        }
+        return 0;
+    }
     // --- Canonical: fixture of tests/test_canonical.cpp:12-22
     const Eigen::MatrixXd A = mat(2, 4, {1, 2, 1, 0, 3, 4, 0, 1});
     Eigen::VectorXd b(2); b[0] = 5; b[1] = 6;

@@ -134,6 +134,63 @@ def test_print_layouts_equal_the_reference():
     assert out.returncode == 0 and out.stdout.split("---\n") == want
 
 
+def test_parser_fuzz_equals_the_reference():
+    """Random line soups from the format's vocabulary: the Python parser accepts, rejects and reads exactly what the
+    reference's parser does (the C++ one shares its structure and is pinned by the fixed cases above)."""
+    from hypothesis import given, settings, strategies as st
+    words = ["maximize", "max", "minimize", "min", "objective:", "objective", "constraints:", "constraints", "subject to:",
+             "subject to", "", "# note", "1 2 3", "4 5 6 7", "1.5 -2 3e1", "0 0", "7", "1 2 # tail", "  3   4  ", "x 1 2", "1 x 2",
+             "-1 -2 -3", ".5 .25 8", "1e-3 2 3 4", "maximise", "Objective:", "2 3"]
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.lists(st.sampled_from(words), min_size=0, max_size=9), st.sampled_from(["\n", "\r\n"]))
+    def check(lines, eol):
+        text = eol.join(lines) + eol
+        ref, mine = R.parse(text), SymmetricalParser().ParseFromString(text)
+        assert (ref is None) == (mine is None), text
+        if ref is not None:
+            same_problem(ref, mine)
+
+    check()
+
+
+def test_cpp_parser_fuzz_equals_the_reference(tmp_path):
+    """The same soups through the C++ parser (cpp/tests/host_tests --parse): 150 random files in one process."""
+    import subprocess
+    rng = np.random.default_rng(3)
+    words = ["maximize", "max", "minimize", "min", "objective:", "objective", "constraints:", "constraints", "subject to:",
+             "subject to", "", "# note", "1 2 3", "4 5 6 7", "1.5 -2 3e1", "0 0", "7", "1 2 # tail", "  3   4  ", "x 1 2", "1 x 2",
+             "-1 -2 -3", ".5 .25 8", "1e-3 2 3 4", "maximise", "Objective:", "2 3"]
+    texts, files = [], []
+    for k in range(150):
+        lines = [words[i] for i in rng.integers(0, len(words), size=int(rng.integers(0, 10)))]
+        if k % 3 == 0:                                      # make a good share of them well-formed
+            rows4 = ["4 5 6 7", "1e-3 2 3 4", "1 2 3 4 # c", "-1 -2 -3 9", "  0 0 1 .5"]
+            lines = ["max" if k % 2 else "minimize", "objective:", "1 2 3", "constraints:"] + \
+                    [rows4[i] for i in rng.integers(0, len(rows4), size=int(rng.integers(1, 5)))] + (lines[:1] if k % 9 == 0 else [])
+        texts.append("\n".join(lines) + "\n")
+        files.append(tmp_path / f"lp{k}.txt")
+        files[-1].write_text(texts[-1])
+    cpp = os.path.join(ROOT, "simplexmethod_b200", "cpp")
+    subprocess.check_call(["make", "-C", cpp, "-s"])
+    out = subprocess.run([os.path.join(cpp, "build", "host_tests"), "--parse"] + [str(f) for f in files], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = out.stdout.splitlines()
+    assert len(got) == len(texts)
+    n_ok = 0
+    for text, line in zip(texts, got):
+        ref = R.parse(text)
+        assert (ref is None) == (line == "null"), text
+        if ref is not None:
+            n_ok += 1
+            v = [float(t) for t in line.split()]
+            m, n = int(v[1]), int(v[2])
+            assert bool(v[0]) == ref["maximize"] and (m, n) == ref["A"].shape
+            assert v[3:3 + m * n] == ref["A"].ravel().tolist() and v[3 + m * n:3 + m * n + m] == ref["b"].tolist()
+            assert v[3 + m * n + m:] == ref["c"].tolist()
+    assert n_ok >= 20
+
+
 # ---- per basis: the reference's QR-based primitives vs the oracle's frozen GE --------------------
 
 @pytest.mark.parametrize("name", sorted(TINY))
