@@ -6,11 +6,16 @@
  * __graft_entry__.smoke() check and bench.py's cpu_baseline / --impl reference
  * legs may use it, and there only as the checker / the CPU arm.
  *
- * PARITY STATUS: "parity unpinned" against the reference's own code.  The
- * reference's EnumerationSolver is an empty stub (src/EnumerationSolver.h:3-10)
- * and its per-basis primitives need Eigen 3.4.0 (CMakeLists.txt:12-17,
- * FetchContent, not vendored, not on this box), so neither can be compiled or
- * run here.  What pins this file instead (tests/test_oracle_*.py):
+ * PARITY STATUS: pinned to the reference's own code paths; the bits of real
+ * Eigen stay unpinned.  The reference's EnumerationSolver is an empty stub
+ * (src/EnumerationSolver.h:3-10) and its per-basis primitives need Eigen 3.4.0
+ * (CMakeLists.txt:12-17, FetchContent, not vendored, not on this box).  What
+ * pins this file (tests/test_oracle_*.py, tests/test_reference_code.py):
+ *   - oracle/_ref: the reference's own Canonical / Solver sources compiled from
+ *     where they lie against an Eigen API stand-in (oracle/eigen_shim), and the
+ *     enumeration composed from them (ref_driver.cpp): class of every basis,
+ *     counters, optimum on the tiny LPs, dense (4,12)...(8,24) and windows of
+ *     the headline LP (x and z to 1e-9: QR there, GE here);
  *   - exact-rational goldens for the reference's own fixtures
  *     (input_symmetric.txt, src/main.cpp:48-57, tests/test_canonical.cpp:12-22
  *     incl. its EXPECT_DOUBLE_EQ pin :52-57) and Beale's LP, tests/golden/;
@@ -49,6 +54,12 @@
  *   z = 0;  for j = m-1..0:  z = fma(c[S[j]], x[j], z)
  *   key = maximize ? -z : z
  *   best is replaced iff key < best_key, or key == best_key and rank < best_rank
+ *
+ * ENUMGPU_PIVOT_RELATIVE (options.pivot_rule; the Eigen-like rule, cf.
+ * FullPivLU::isInvertible at SimplexSolover.h:124-126): in the loop above the
+ * test becomes  if !(|M[p][k]| > 0) -> SINGULAR  and the elimination runs to the
+ * end, tracking pmax = max_k |pivot_k|, pmin = min_k |pivot_k|; afterwards
+ *   if !(pmin > eps_rel * pmax) -> SINGULAR      (eps_rel = eps_piv, default m*2^-52)
  */
 #define _GNU_SOURCE
 #include "enumcpu.h"
@@ -131,6 +142,15 @@ static int next_subset(int n, int m, int32_t* S)
 int enumcpu_eval_basis(const enumgpu_problem* p, double eps_feas, double thr,
                        const int32_t* S, double* x, double* z_out)
 {
+    return enumcpu_eval_basis_rule(p, eps_feas, ENUMGPU_PIVOT_ABSOLUTE, thr, S, x, z_out);
+}
+
+/* rule ABSOLUTE: tol = thr = eps_piv * max|A|;  rule RELATIVE: tol = eps_rel */
+int enumcpu_eval_basis_rule(const enumgpu_problem* p, double eps_feas, int rule, double tol,
+                            const int32_t* S, double* x, double* z_out)
+{
+    const double thr = (rule == ENUMGPU_PIVOT_RELATIVE) ? 0.0 : tol;
+    double pmax = 0.0, pmin = INFINITY;
     const int m = p->m, lda = p->lda;
     double M[ENUMGPU_MAX_M][ENUMGPU_MAX_M + 1];
     double rinv[ENUMGPU_MAX_M], t[ENUMGPU_MAX_M];
@@ -149,6 +169,8 @@ int enumcpu_eval_basis(const enumgpu_problem* p, double eps_feas, double thr,
             if (v > best) { best = v; piv = r; }
         }
         if (!(best > thr)) return ENUMCPU_SINGULAR;
+        if (best > pmax) pmax = best;
+        if (best < pmin) pmin = best;
         if (piv != k)
             for (int j = k; j <= m; ++j) { double s = M[k][j]; M[k][j] = M[piv][j]; M[piv][j] = s; }
         rinv[k] = 1.0 / M[k][k];
@@ -157,6 +179,7 @@ int enumcpu_eval_basis(const enumgpu_problem* p, double eps_feas, double thr,
             for (int j = k + 1; j <= m; ++j) M[r][j] = fma(-l, M[k][j], M[r][j]);
         }
     }
+    if (rule == ENUMGPU_PIVOT_RELATIVE && !(pmin > tol * pmax)) return ENUMCPU_SINGULAR;
     for (int i = 0; i < m; ++i) t[i] = M[i][m];
     for (int j = m - 1; j >= 0; --j) {
         x[j] = t[j] * rinv[j];
@@ -186,8 +209,14 @@ double enumcpu_scale(const enumgpu_problem* p)
 
 typedef struct {
     const enumgpu_problem* p;
-    double eps_feas, thr;
+    double eps_feas, thr;      /* thr: absolute threshold, or eps_rel under the relative rule */
+    int rule;
     uint64_t begin, end;
+    /* optional listing of the ranks of one class (shared by all threads) */
+    int list_cls;              /* -1: none */
+    uint64_t* list_out;
+    uint64_t list_cap;
+    uint64_t* list_count;      /* atomic */
     /* out */
     double best_key;
     uint64_t best_rank, n_sing, n_infeas, n_feas;
@@ -206,8 +235,12 @@ static void* scan_range(void* arg)
     if (J->begin >= J->end) return NULL;
     enumcpu_unrank(p->n, p->m, J->begin, S);
     for (uint64_t r = J->begin; r < J->end; ++r) {
-        int st = enumcpu_eval_basis(p, J->eps_feas, J->thr, S, x, &z);
+        int st = enumcpu_eval_basis_rule(p, J->eps_feas, J->rule, J->thr, S, x, &z);
         if (J->status_out) J->status_out[r - J->status_base] = (uint8_t)st;
+        if (st == J->list_cls) {
+            uint64_t pos = __atomic_fetch_add(J->list_count, 1, __ATOMIC_RELAXED);
+            if (pos < J->list_cap) J->list_out[pos] = r;
+        }
         if (st == ENUMCPU_SINGULAR) ++J->n_sing;
         else if (st == ENUMCPU_INFEASIBLE) ++J->n_infeas;
         else {
@@ -237,20 +270,36 @@ static int check_problem(const enumgpu_problem* p)
     return 0;
 }
 
+static int cmp_u64(const void* a, const void* b)
+{
+    uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+    return x < y ? -1 : x > y;
+}
+
 int enumcpu_solve_ex(const enumgpu_problem* p, const enumgpu_options* o, int n_threads,
                      uint8_t* status_out, enumgpu_result* out)
+{
+    return enumcpu_solve_list(p, o, n_threads, status_out, -1, NULL, 0, NULL, out);
+}
+
+int enumcpu_solve_list(const enumgpu_problem* p, const enumgpu_options* o, int n_threads, uint8_t* status_out,
+                       int list_cls, uint64_t* list_out, uint64_t list_cap, uint64_t* n_listed, enumgpu_result* out)
 {
     memset(out, 0, sizeof *out);
     int rc = check_problem(p);
     if (rc) { out->status = rc; return rc; }
     uint64_t total = enumcpu_binomial(p->n, p->m);
     if (total == 0) { out->status = ENUMGPU_ERR_RANGE; return out->status; }
+    const int rule = o ? o->pivot_rule : ENUMGPU_PIVOT_ABSOLUTE;
+    if (rule != ENUMGPU_PIVOT_ABSOLUTE && rule != ENUMGPU_PIVOT_RELATIVE) { out->status = ENUMGPU_ERR_ARG; return out->status; }
     double eps_feas = (o && o->eps_feas >= 0) ? o->eps_feas : 1e-9;
-    double eps_piv  = (o && o->eps_piv  >= 0) ? o->eps_piv  : 1e-9;
+    double eps_piv  = (o && o->eps_piv  >= 0) ? o->eps_piv
+                    : (rule == ENUMGPU_PIVOT_RELATIVE ? (double)p->m * 0x1p-52 : 1e-9);
     uint64_t begin = o ? o->rank_begin : 0, end = o ? o->rank_end : 0;
     if (begin == 0 && end == 0) end = total;
     if (begin > end || end > total) { out->status = ENUMGPU_ERR_RANGE; return out->status; }
-    double thr = eps_piv * enumcpu_scale(p);
+    double thr = (rule == ENUMGPU_PIVOT_RELATIVE) ? eps_piv : eps_piv * enumcpu_scale(p);
+    uint64_t listed = 0;
 
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 256) n_threads = 256;
@@ -262,7 +311,9 @@ int enumcpu_solve_ex(const enumgpu_problem* p, const enumgpu_options* o, int n_t
     scan_job* jobs = (scan_job*)calloc((size_t)n_threads, sizeof(scan_job));
     pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
     for (int i = 0; i < n_threads; ++i) {
-        jobs[i].p = p; jobs[i].eps_feas = eps_feas; jobs[i].thr = thr;
+        jobs[i].p = p; jobs[i].eps_feas = eps_feas; jobs[i].thr = thr; jobs[i].rule = rule;
+        jobs[i].list_cls = list_out || n_listed ? list_cls : -1; jobs[i].list_out = list_out; jobs[i].list_cap = list_out ? list_cap : 0;
+        jobs[i].list_count = &listed;
         jobs[i].begin = begin + span / (uint64_t)n_threads * (uint64_t)i
                       + ((uint64_t)i < span % (uint64_t)n_threads ? (uint64_t)i : span % (uint64_t)n_threads);
         jobs[i].status_out = status_out; jobs[i].status_base = begin;
@@ -282,6 +333,8 @@ int enumcpu_solve_ex(const enumgpu_problem* p, const enumgpu_options* o, int n_t
         }
     }
     free(jobs); free(th);
+    if (n_listed) *n_listed = listed;
+    if (list_out) qsort(list_out, (size_t)(listed < list_cap ? listed : list_cap), sizeof(uint64_t), cmp_u64);
 
     out->m = p->m;
     out->n_bases = span;
@@ -292,7 +345,7 @@ int enumcpu_solve_ex(const enumgpu_problem* p, const enumgpu_options* o, int n_t
     if (best_rank == UINT64_MAX) { out->status = ENUMGPU_NO_FEASIBLE; out->objective = NAN; return out->status; }
     enumcpu_unrank(p->n, p->m, best_rank, out->basis);
     double z;
-    enumcpu_eval_basis(p, eps_feas, thr, out->basis, out->x_B, &z);
+    enumcpu_eval_basis_rule(p, eps_feas, rule, thr, out->basis, out->x_B, &z);
     out->objective = z;
     out->status = ENUMGPU_OK;
     return out->status;

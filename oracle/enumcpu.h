@@ -28,6 +28,11 @@ double   enumcpu_scale(const enumgpu_problem* p);
 int      enumcpu_eval_basis(const enumgpu_problem* p, double eps_feas, double thr,
                             const int32_t* S, double* x, double* z);
 
+/* same with the singularity rule of enumgpu_options.pivot_rule: tol = eps_piv*scale (ENUMGPU_PIVOT_ABSOLUTE)
+ * or the relative threshold eps_rel (ENUMGPU_PIVOT_RELATIVE: min|pivot| > eps_rel * max|pivot|) */
+int      enumcpu_eval_basis_rule(const enumgpu_problem* p, double eps_feas, int rule, double tol,
+                                 const int32_t* S, double* x, double* z);
+
 /* single-threaded enumeration of the rank range */
 int      enumcpu_solve(const enumgpu_problem* p, const enumgpu_options* o, enumgpu_result* out);
 
@@ -35,6 +40,12 @@ int      enumcpu_solve(const enumgpu_problem* p, const enumgpu_options* o, enumg
  * one ENUMCPU_* byte per rank of the range; out->kernel_ms = wall time */
 int      enumcpu_solve_ex(const enumgpu_problem* p, const enumgpu_options* o, int n_threads,
                           uint8_t* status_out, enumgpu_result* out);
+
+/* enumcpu_solve_ex that also lists the ranks (ascending) of the bases of class list_cls (ENUMCPU_*; -1 = none):
+ * list_out (may be NULL) gets at most list_cap of them, *n_listed (may be NULL) their full number */
+int      enumcpu_solve_list(const enumgpu_problem* p, const enumgpu_options* o, int n_threads, uint8_t* status_out,
+                            int list_cls, uint64_t* list_out, uint64_t list_cap, uint64_t* n_listed,
+                            enumgpu_result* out);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,13 @@ def lib():
         L.enumcpu_solve_ex.restype = C.c_int
         L.enumcpu_solve_ex.argtypes = [C.POINTER(_abi.Problem), C.POINTER(_abi.Options), C.c_int,
                                        C.POINTER(C.c_uint8), C.POINTER(_abi.Result)]
+        L.enumcpu_eval_basis_rule.restype = C.c_int
+        L.enumcpu_eval_basis_rule.argtypes = [C.POINTER(_abi.Problem), C.c_double, C.c_int, C.c_double,
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.enumcpu_solve_list.restype = C.c_int
+        L.enumcpu_solve_list.argtypes = [C.POINTER(_abi.Problem), C.POINTER(_abi.Options), C.c_int, C.POINTER(C.c_uint8),
+                                         C.c_int, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64),
+                                         C.POINTER(_abi.Result)]
         _LIB = L
     return _LIB
 
@@ -64,8 +71,8 @@ class HostProblem:
                                    self.A.ctypes.data, self.b.ctypes.data, self.c.ctypes.data)
 
 
-def make_options(eps_feas=-1.0, eps_piv=-1.0, rank_begin=0, rank_end=0, algo=0):
-    return _abi.Options(eps_feas, eps_piv, rank_begin, rank_end, 0, algo, None, None)
+def make_options(eps_feas=-1.0, eps_piv=-1.0, rank_begin=0, rank_end=0, algo=0, pivot_rule=0):
+    return _abi.Options(eps_feas, eps_piv, rank_begin, rank_end, 0, algo, None, None, 0, 0, pivot_rule, 0)
 
 
 def solve(A, b, c, maximize, n_threads=1, want_status=False, **opt):
@@ -86,11 +93,27 @@ def solve(A, b, c, maximize, n_threads=1, want_status=False, **opt):
     return res, status
 
 
-def eval_basis(A, b, c, maximize, S, eps_feas=1e-9, eps_piv=1e-9):
+def list_class(A, b, c, maximize, cls, capacity=1 << 20, n_threads=1, **opt):
+    """Enumerate and list the ranks (ascending) of the bases of class `cls` (FEASIBLE / INFEASIBLE / SINGULAR).
+    Returns (Result, ranks uint64 array, full count)."""
     hp = HostProblem(A, b, c, maximize)
-    thr = eps_piv * lib().enumcpu_scale(C.byref(hp.struct))
+    o = make_options(**opt)
+    res = _abi.Result()
+    ranks = np.zeros(max(int(capacity), 1), dtype=np.uint64)
+    n_listed = C.c_uint64()
+    lib().enumcpu_solve_list(C.byref(hp.struct), C.byref(o), int(n_threads), None, int(cls),
+                             ranks.ctypes.data_as(C.POINTER(C.c_uint64)), int(capacity), C.byref(n_listed), C.byref(res))
+    return res, ranks[: min(n_listed.value, int(capacity))].copy(), n_listed.value
+
+
+def eval_basis(A, b, c, maximize, S, eps_feas=1e-9, eps_piv=None, pivot_rule=0):
+    hp = HostProblem(A, b, c, maximize)
+    if pivot_rule == _abi.PIVOT_RELATIVE:
+        tol = hp.m * 2.0 ** -52 if eps_piv is None else eps_piv
+    else:
+        tol = (1e-9 if eps_piv is None else eps_piv) * lib().enumcpu_scale(C.byref(hp.struct))
     Sv = (C.c_int32 * hp.m)(*S)
     x = (C.c_double * hp.m)()
     z = C.c_double()
-    st = lib().enumcpu_eval_basis(C.byref(hp.struct), eps_feas, thr, Sv, x, C.byref(z))
+    st = lib().enumcpu_eval_basis_rule(C.byref(hp.struct), eps_feas, int(pivot_rule), tol, Sv, x, C.byref(z))
     return st, list(x), z.value

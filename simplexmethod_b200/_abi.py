@@ -21,6 +21,9 @@ ALGO_AUTO = 0
 ALGO_INDEPENDENT = 1
 ALGO_SHARED = 2
 
+PIVOT_ABSOLUTE = 0
+PIVOT_RELATIVE = 1
+
 UINT64_MAX = (1 << 64) - 1
 
 
@@ -39,6 +42,7 @@ class Options(C.Structure):
         ("devices", C.POINTER(C.c_int32)),
         ("stream", C.c_void_p),
         ("shard_index", C.c_int32), ("shard_count", C.c_int32),
+        ("pivot_rule", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -91,6 +95,15 @@ SYMBOLS = {
     "enumgpu_merge_partial": (None, [C.POINTER(Partial), C.POINTER(Partial)]),
     "enumgpu_shard_begin": (C.c_uint64, [C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32]),
     "enumgpu_fp64_peak_tflops": (C.c_double, [C.c_int32]),
+    "enumgpu_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
+    "enumgpu_destroy": (None, [C.c_void_p]),
+    "enumgpu_solve_h": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.POINTER(Options), C.POINTER(Result)]),
+    "enumgpu_solve_hv": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(Problem), C.POINTER(Options),
+                                    C.POINTER(Result)]),
+    "enumgpu_enqueue_h": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.c_double, C.POINTER(Options), C.c_void_p,
+                                     C.POINTER(C.c_int32)]),
+    "enumgpu_handle_stream": (C.c_void_p, [C.c_void_p]),
+    "enumgpu_selftest_rcp": (C.c_int, [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
 }
 
 

@@ -19,6 +19,7 @@
 #ifndef ENUMGPU_HAVE_EIGEN
 #include <cstddef>
 #include <initializer_list>
+#include <limits>
 #include <stdexcept>
 #include <vector>
 
@@ -26,12 +27,17 @@ namespace Eigen {
 
 using Index = std::ptrdiff_t;
 
+// Real Eigen leaves MatrixXd(r, c) / VectorXd(n) UNINITIALISED; only Zero() / Identity() define the contents.
+// The shim fills plain constructions with NaN so that code relying on zero-initialisation fails here, in the
+// tests, and not silently once the real <Eigen/Dense> is on the include path.
+namespace shim_detail { inline double poison() { return std::numeric_limits<double>::quiet_NaN(); } }
+
 class VectorXd {
 public:
     VectorXd() = default;
-    explicit VectorXd(Index n) : v_(static_cast<size_t>(n), 0.0) {}
+    explicit VectorXd(Index n) : v_(static_cast<size_t>(n), shim_detail::poison()) {}
     VectorXd(std::initializer_list<double> il) : v_(il) {}
-    static VectorXd Zero(Index n) { return VectorXd(n); }
+    static VectorXd Zero(Index n) { VectorXd r(n); for (auto& x : r.v_) x = 0.0; return r; }
     Index size() const { return static_cast<Index>(v_.size()); }
     double* data() { return v_.data(); }
     const double* data() const { return v_.data(); }
@@ -57,11 +63,11 @@ private:
 class MatrixXd {
 public:
     MatrixXd() = default;
-    MatrixXd(Index r, Index c) : r_(r), c_(c), v_(static_cast<size_t>(r * c), 0.0) {}
-    static MatrixXd Zero(Index r, Index c) { return MatrixXd(r, c); }
+    MatrixXd(Index r, Index c) : r_(r), c_(c), v_(static_cast<size_t>(r * c), shim_detail::poison()) {}
+    static MatrixXd Zero(Index r, Index c) { MatrixXd m(r, c); for (auto& x : m.v_) x = 0.0; return m; }
     static MatrixXd Identity(Index r, Index c)
     {
-        MatrixXd m(r, c);
+        MatrixXd m = Zero(r, c);
         for (Index i = 0; i < (r < c ? r : c); ++i) m(i, i) = 1.0;
         return m;
     }

@@ -13,6 +13,10 @@
 // Errors: std::invalid_argument for bad dimensions (cf. Canonical.cpp:27-46),
 // std::runtime_error when no basis is feasible (cf. SimplexSolover.h:371) or
 // the CUDA side fails.
+// Like Solver, which keeps its working state in the object (SimplexSolover.h:12),
+// the solver keeps an enumgpu_handle per device from its first solve() on:
+// stream, events, pinned staging and device buffers are created once, so a
+// solve is one H2D copy, one kernel launch and one D2H copy.
 #pragma once
 
 #include <cstdint>
@@ -33,8 +37,15 @@ public:
             throw std::invalid_argument("EnumerationSolver: (m, n) outside the limits of libenumgpu");
     }
 
+    ~EnumerationSolver() { release(); }
+    EnumerationSolver(const EnumerationSolver& o)
+        : problem_(o.problem_), devices_(o.devices_), algo_(o.algo_), rule_(o.rule_), eps_feas_(o.eps_feas_), eps_piv_(o.eps_piv_),
+          rank_begin_(o.rank_begin_), rank_end_(o.rank_end_), res_(o.res_), solved_(o.solved_) {}      // handles are not shared
+    EnumerationSolver& operator=(const EnumerationSolver&) = delete;
+
     // optional knobs (not in the reference)
-    void setDevices(const std::vector<int>& cuda_ordinals) { devices_.assign(cuda_ordinals.begin(), cuda_ordinals.end()); }
+    void setDevices(const std::vector<int>& cuda_ordinals) { release(); devices_.assign(cuda_ordinals.begin(), cuda_ordinals.end()); }
+    void setPivotRule(int enumgpu_pivot_rule) { rule_ = enumgpu_pivot_rule; }    // ENUMGPU_PIVOT_ABSOLUTE (default) / _RELATIVE
     void setAlgorithm(int enumgpu_algo) { algo_ = enumgpu_algo; }
     void setTolerances(double eps_feas, double eps_piv) { eps_feas_ = eps_feas; eps_piv_ = eps_piv; }
     void setRankRange(uint64_t begin, uint64_t end) { rank_begin_ = begin; rank_end_ = end; }
@@ -53,10 +64,11 @@ public:
         enumgpu_options o{};
         o.eps_feas = eps_feas_; o.eps_piv = eps_piv_;
         o.rank_begin = rank_begin_; o.rank_end = rank_end_;
-        o.n_devices = static_cast<int32_t>(devices_.size());
-        o.devices = devices_.empty() ? nullptr : devices_.data();
         o.algo = algo_;
-        const int rc = enumgpu_solve(&p, &o, &res_);
+        o.pivot_rule = rule_;
+        int rc = acquire();
+        if (rc == ENUMGPU_OK) rc = enumgpu_solve_hv(handles_.data(), static_cast<int32_t>(handles_.size()), &p, &o, &res_);
+        else res_.status = rc;
         solved_ = true;
         if (rc == ENUMGPU_ERR_CUDA) throw std::runtime_error(std::string("libenumgpu: ") + enumgpu_last_error());
         if (rc < 0) throw std::invalid_argument(std::string("libenumgpu: ") + enumgpu_last_error());
@@ -81,10 +93,28 @@ public:
 
 private:
     void need() const { if (!solved_) throw std::logic_error("EnumerationSolver: solve() has not been called"); }
+    int acquire()
+    {
+        if (!handles_.empty()) return ENUMGPU_OK;
+        const size_t nd = devices_.empty() ? 1 : devices_.size();
+        for (size_t i = 0; i < nd; ++i) {
+            enumgpu_handle* h = nullptr;
+            const int rc = enumgpu_create(devices_.empty() ? -1 : devices_[i], &h);
+            if (rc != ENUMGPU_OK) { release(); return rc; }
+            handles_.push_back(h);
+        }
+        return ENUMGPU_OK;
+    }
+    void release()
+    {
+        for (enumgpu_handle* h : handles_) enumgpu_destroy(h);
+        handles_.clear();
+    }
 
     Canonical problem_;
     std::vector<int32_t> devices_;
-    int algo_ = ENUMGPU_ALGO_AUTO;
+    std::vector<enumgpu_handle*> handles_;
+    int algo_ = ENUMGPU_ALGO_AUTO, rule_ = ENUMGPU_PIVOT_ABSOLUTE;
     double eps_feas_ = -1.0, eps_piv_ = -1.0;
     uint64_t rank_begin_ = 0, rank_end_ = 0;
     enumgpu_result res_{};

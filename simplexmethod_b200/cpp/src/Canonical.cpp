@@ -89,7 +89,7 @@ bool Canonical::IsFeasibleBasis() const
 std::unique_ptr<Canonical> Canonical::GetDual() const
 {
     const auto m = A_.rows(), n = A_.cols();
-    Eigen::MatrixXd Ad(n, 2 * m + n);
+    Eigen::MatrixXd Ad = Eigen::MatrixXd::Zero(n, 2 * m + n);     // real Eigen does not zero MatrixXd(r, c)
     Eigen::VectorXd cd = Eigen::VectorXd::Zero(2 * m + n);
     for (Eigen::Index j = 0; j < n; ++j) {
         for (Eigen::Index i = 0; i < m; ++i) {

@@ -44,7 +44,7 @@ std::unique_ptr<Canonical> Symmetrical::ToCanonical() const
     // min: Ax - s + a = b with surplus s and artificial a; artificials form the
     // basis and, as in the reference, carry zero cost.
     const auto extra = maximize_ ? m : 2 * m;
-    Eigen::MatrixXd Ac(m, n + extra);
+    Eigen::MatrixXd Ac = Eigen::MatrixXd::Zero(m, n + extra);      // real Eigen does not zero MatrixXd(r, c)
     Eigen::VectorXd cc = Eigen::VectorXd::Zero(n + extra);
     for (Eigen::Index j = 0; j < n; ++j) {
         cc[j] = c_[j];

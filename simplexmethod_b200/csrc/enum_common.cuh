@@ -22,6 +22,17 @@ constexpr int kMaxN = ENUMGPU_MAX_N;
 constexpr int kBinomRows = kMaxN + 1;   // top index 0..64
 constexpr int kBinomCols = kMaxM + 1;   // k index 0..16
 
+struct BlockPartial;
+
+// Per-enqueue control block in device memory, zero before the first launch of an enqueue and zero again
+// after its last block has finished (that block resets it): the work counter of k_shared and the ticket
+// that tells a finishing block whether it is the last one of the whole enqueue.
+struct Ctrl {
+    unsigned long long unit_counter;
+    unsigned int ticket;
+    unsigned int pad_;
+};
+
 // Everything a kernel needs besides the matrix data.  Passed by value.
 struct LaunchParams {
     const double* A;        // device, column-major
@@ -40,6 +51,17 @@ struct LaunchParams {
     unsigned long long* list_count;
     uint64_t* list_ranks;
     uint64_t  list_cap;
+    // singularity rule: ENUMGPU_PIVOT_ABSOLUTE (thr above) or ENUMGPU_PIVOT_RELATIVE (thr = 0, rel_eps below;
+    // the run-time-m kernels only)
+    int32_t  pivot_rule;
+    int32_t  algo_used;     // written to the record
+    double   rel_eps;
+    // fused finalize: the last block of the enqueue (ticket == total_blocks - 1) reduces all_parts[0..total_blocks)
+    // into *record and resets *ctrl
+    Ctrl*            ctrl;
+    BlockPartial*    all_parts;
+    uint32_t         total_blocks;
+    enumgpu_partial* record;
 };
 
 __device__ __forceinline__ void list_append(unsigned long long* count, uint64_t* ranks, uint64_t cap, uint64_t rank)
@@ -143,10 +165,12 @@ __device__ __forceinline__ void unrank_lex(const uint64_t* __restrict__ binom, i
 // One basis with run-time m (local-memory arrays): used once per enqueue, by
 // one thread, to materialise x_B / objective of the winning basis on the device.
 __device__ inline int eval_basis_generic(const double* A, int lda, const double* b, const double* c, int m,
-                                  const int* S, double thr, double eps_feas, double* x, double* z_out)
+                                  const int* S, double thr, double eps_feas, double* x, double* z_out,
+                                  int pivot_rule = ENUMGPU_PIVOT_ABSOLUTE, double rel_eps = 0.0)
 {
     double Mx[kMaxM][kMaxM + 1];
     double rinv[kMaxM];
+    double pmax = 0.0, pmin = __longlong_as_double(0x7ff0000000000000LL);
     for (int j = 0; j < m; ++j)
         for (int r = 0; r < m; ++r) Mx[r][j] = A[r + (size_t)S[j] * lda];
     for (int r = 0; r < m; ++r) Mx[r][m] = b[r];
@@ -158,6 +182,8 @@ __device__ inline int eval_basis_generic(const double* A, int lda, const double*
             if (v > best) { best = v; p = r; }
         }
         if (!(best > thr)) return 2;
+        if (best > pmax) pmax = best;
+        if (best < pmin) pmin = best;
         if (p != k)
             for (int j = k; j <= m; ++j) { const double t = Mx[k][j]; Mx[k][j] = Mx[p][j]; Mx[p][j] = t; }
         rinv[k] = __drcp_rn(Mx[k][k]);
@@ -166,6 +192,7 @@ __device__ inline int eval_basis_generic(const double* A, int lda, const double*
             for (int j = k + 1; j <= m; ++j) Mx[r][j] = fnma(l, Mx[k][j], Mx[r][j]);
         }
     }
+    if (pivot_rule == ENUMGPU_PIVOT_RELATIVE && !(pmin > __dmul_rn(rel_eps, pmax))) return 2;
     bool infeasible = false;
     double z = 0.0;
     for (int j = m - 1; j >= 0; --j) {
@@ -176,6 +203,113 @@ __device__ inline int eval_basis_generic(const double* A, int lda, const double*
     }
     *z_out = z;
     return infeasible ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// Fused finalize.  Every block of an enqueue (which may consist of up to three launches on one stream: the
+// shared kernel and the independent kernel on the ragged head and tail of the range) calls this after it has
+// written its BlockPartial.  The block that draws the last ticket reduces all partials, writes the 256-byte
+// record — x_B and the objective of the winning basis re-evaluated on the device by warp 0, lane j owning
+// column j of [B | b]: every element receives the same operations in the same order as in
+// eval_basis_generic — and resets the control block for the next enqueue.  `scratch`: >= kFinalizeScratch bytes
+// of shared memory that the block no longer needs (8-byte aligned).  blockDim.x: a multiple of 32, <= 1024.
+constexpr int kFinalizeScratch = 8 * (kMaxM * (kMaxM + 1) + kMaxM) + 4 * kMaxM + 32 * 40 + 16;
+
+__device__ __forceinline__ void finalize_if_last(const LaunchParams& prm, unsigned char* scratch)
+{
+    __shared__ int s_is_last;
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // this block's partial is visible before its ticket
+        const unsigned t = atomicAdd(&prm.ctrl->ticket, 1u);
+        s_is_last = (t + 1u == prm.total_blocks);
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+
+    double*   s_M    = reinterpret_cast<double*>(scratch);                 // [kMaxM][kMaxM+1]
+    double*   s_rinv = s_M + kMaxM * (kMaxM + 1);                          // [kMaxM]
+    int*      s_S    = reinterpret_cast<int*>(s_rinv + kMaxM);             // [kMaxM]
+    double*   s_wkey = reinterpret_cast<double*>(s_S + kMaxM);             // [32]
+    uint64_t* s_wrank = reinterpret_cast<uint64_t*>(s_wkey + 32);          // [32]
+    uint64_t* s_wcnt = s_wrank + 32;                                       // [3][32]
+    uint64_t* s_best = s_wcnt + 96;                                        // [1] winning rank
+    constexpr int kLd = kMaxM + 1;
+
+    double   key = __longlong_as_double(0x7ff0000000000000LL);
+    uint64_t rank = ~0ull, cs = 0, ci = 0, cf = 0;
+    for (uint32_t i = threadIdx.x; i < prm.total_blocks; i += blockDim.x) {
+        const BlockPartial* bp = prm.all_parts + i;
+        const double k2 = __ldcg(&bp->key);
+        const uint64_t r2 = __ldcg(&bp->rank);
+        if (better(k2, r2, key, rank)) { key = k2; rank = r2; }
+        cs += __ldcg(&bp->n_sing); ci += __ldcg(&bp->n_infeas); cf += __ldcg(&bp->n_feas);
+    }
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double   k2 = __shfl_down_sync(full, key, off);
+        const uint64_t r2 = __shfl_down_sync(full, rank, off);
+        if (better(k2, r2, key, rank)) { key = k2; rank = r2; }
+        cs += __shfl_down_sync(full, cs, off);
+        ci += __shfl_down_sync(full, ci, off);
+        cf += __shfl_down_sync(full, cf, off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (int)(blockDim.x >> 5);
+    if (lane == 0) { s_wkey[warp] = key; s_wrank[warp] = rank; s_wcnt[warp] = cs; s_wcnt[32 + warp] = ci; s_wcnt[64 + warp] = cf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < n_warps; ++w) {
+            if (better(s_wkey[w], s_wrank[w], key, rank)) { key = s_wkey[w]; rank = s_wrank[w]; }
+            cs += s_wcnt[w]; ci += s_wcnt[32 + w]; cf += s_wcnt[64 + w];
+        }
+        enumgpu_partial* r = prm.record;
+        r->key = key; r->best_rank = rank;
+        r->n_bases = cs + ci + cf;                         // every visited rank is in exactly one class
+        r->n_singular = cs; r->n_infeasible = ci; r->n_feasible = cf;
+        r->m = prm.m; r->algo_used = prm.algo_used;
+        for (int i = 0; i < kMaxM; ++i) { r->x_B[i] = 0.0; r->basis[i] = 0; }
+        r->objective = __longlong_as_double(0x7ff8000000000000LL);
+        s_best[0] = rank;
+        if (rank != ~0ull) unrank_lex(prm.binom, prm.n, prm.m, rank, s_S);
+        prm.ctrl->unit_counter = 0ull;                     // ready for the next enqueue on this control block
+        prm.ctrl->ticket = 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32 && s_best[0] != ~0ull) {
+        const int m = prm.m;
+        if (lane <= m)
+            for (int r = 0; r < m; ++r) s_M[r * kLd + lane] = lane < m ? prm.A[r + (size_t)s_S[lane] * prm.lda] : prm.b[r];
+        __syncwarp();
+        for (int k = 0; k < m; ++k) {
+            int p = k;                                       // first maximum of |M[r][k]|, r >= k (uniform)
+            double best = fabs(s_M[k * kLd + k]);
+            for (int r = k + 1; r < m; ++r) {
+                const double v = fabs(s_M[r * kLd + k]);
+                if (v > best) { best = v; p = r; }
+            }
+            __syncwarp();
+            if (p != k && lane >= k && lane <= m) { const double t = s_M[k * kLd + lane]; s_M[k * kLd + lane] = s_M[p * kLd + lane]; s_M[p * kLd + lane] = t; }
+            __syncwarp();
+            const double rinv = __drcp_rn(s_M[k * kLd + k]);
+            if (lane == 0) s_rinv[k] = rinv;
+            if (lane > k && lane <= m)
+                for (int r = k + 1; r < m; ++r)
+                    s_M[r * kLd + lane] = fnma(__dmul_rn(s_M[r * kLd + k], rinv), s_M[k * kLd + lane], s_M[r * kLd + lane]);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            enumgpu_partial* r = prm.record;
+            double z = 0.0;
+            for (int j = m - 1; j >= 0; --j) {
+                const double xj = __dmul_rn(s_M[j * kLd + m], s_rinv[j]);
+                for (int i = 0; i < j; ++i) s_M[i * kLd + m] = fnma(s_M[i * kLd + j], xj, s_M[i * kLd + m]);
+                z = __fma_rn(prm.c[s_S[j]], xj, z);
+                r->x_B[j] = xj; r->basis[j] = s_S[j];
+            }
+            r->objective = z;
+        }
+    }
 }
 
 }  // namespace enumgpu

@@ -158,9 +158,11 @@ k_independent(const LaunchParams prm, BlockPartial* __restrict__ partials)
         }
     }
     block_reduce<kIndepThreads>(best_key, best_rank, ns, ni, nf, partials + blockIdx.x);
+    finalize_if_last(prm, smem_raw);      // staged A, b, c are dead: every thread has passed block_reduce's barrier
 }
 
-// Run-time m (local-memory arrays): m above the register-resident range.
+// Run-time m (local-memory arrays): m above the register-resident range, and every m under the
+// relative (Eigen-like) singularity rule.
 __global__ void __launch_bounds__(kIndepThreads)
 k_independent_generic(const LaunchParams prm, BlockPartial* __restrict__ partials)
 {
@@ -191,7 +193,7 @@ k_independent_generic(const LaunchParams prm, BlockPartial* __restrict__ partial
         unrank_lex(sbin, n, m, r0, S);
         for (uint64_t r = r0; r < r1; ++r) {
             double z, x[kMaxM];
-            const int st = eval_basis_generic(sA, m, sb, sc, m, S, prm.thr, prm.eps_feas, x, &z);
+            const int st = eval_basis_generic(sA, m, sb, sc, m, S, prm.thr, prm.eps_feas, x, &z, prm.pivot_rule, prm.rel_eps);
             if (st == 2) ++ns;
             else if (st == 1) ++ni;
             else {
@@ -206,6 +208,7 @@ k_independent_generic(const LaunchParams prm, BlockPartial* __restrict__ partial
         }
     }
     block_reduce<kIndepThreads>(best_key, best_rank, ns, ni, nf, partials + blockIdx.x);
+    finalize_if_last(prm, smem_raw);
 }
 
 }  // namespace enumgpu

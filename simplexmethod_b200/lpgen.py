@@ -109,6 +109,37 @@ def degenerate_lp():
     return A, b, c, False
 
 
+def small_degenerate_lp():
+    """Degenerate m=7, n=18 LP (31 824 bases) for fast sharding / sub-range tests: two Beale blocks (rows 0-2 and
+    3-5), a coupling row x_B3 + x_C3 + slack = 2, and three duplicated / rescaled columns, two of them placed FIRST
+    in the column order: columns 0 and 1 are identical, so every child task whose prefix starts (0, 1, .) is
+    singular as a whole (the shared kernel books such subtrees in bulk), and column 2 = 2 x column 5.
+    All entries dyadic; many exact ties at the optimum."""
+    m = 7
+    cols, cost = [], []
+
+    def beale(blk, j, sc=1.0):
+        v = np.zeros(m)
+        for i in range(3):
+            v[3 * blk + i] = sc * _BEALE_A[i][j]
+        if j == 3:
+            v[6] = sc * 1.0                      # coupling row
+        return v, sc * _BEALE_C[j]
+
+    order = [(0, 0, 1.0), (0, 0, 1.0), (0, 3, 2.0)] + [(0, j, 1.0) for j in range(1, 7)] + [(1, j, 1.0) for j in range(7)]
+    for blk, j, sc in order:
+        v, cj = beale(blk, j, sc)
+        cols.append(v); cost.append(cj)
+    slack = np.zeros(m); slack[6] = 1.0
+    cols.append(slack); cost.append(0.0)
+    v, cj = beale(1, 3, 0.5)
+    cols.append(v); cost.append(cj)
+    A = np.asfortranarray(np.array(cols).T)
+    b = np.array([_BEALE_B[0], _BEALE_B[1], _BEALE_B[2], _BEALE_B[0], _BEALE_B[1], _BEALE_B[2], 2.0])
+    assert A.shape == (7, 18)
+    return A, b, np.array(cost), False
+
+
 def lab_symmetric_canonical():
     """Config 1: the reference's input_symmetric.txt LP after Symmetrical::ToCanonical.
 

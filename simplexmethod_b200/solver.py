@@ -126,7 +126,11 @@ class Canonical:
         return cls.value, list(x), z.value
 
     def GetBasicSolution(self):
-        """x (length n) of the designated basis (reference Canonical.cpp:179-197); singular -> RuntimeError."""
+        """x (length n) of the designated basis (reference Canonical.cpp:179-197), for a Canonical of any size and
+        any index list the constructor accepted.  One documented deviation: the reference's QR solve returns
+        *some* vector for a singular basis without signalling; here a singular basis (repeated indices included)
+        raises RuntimeError("Singular basis matrix"), the convention of the reference's other per-basis solve
+        (Solver::computeBFS, SimplexSolover.h:124-126).  IsFeasibleBasis() never raises: singular -> False."""
         cls, xB, _ = self._eval_designated()
         if cls == 2:
             raise RuntimeError("Singular basis matrix")
@@ -160,7 +164,8 @@ class EnumerationSolver:
     """
 
     def __init__(self, problem: Canonical, devices: Optional[Sequence[int]] = None,
-                 algo: int = _abi.ALGO_AUTO, eps_feas: float = 1e-9, eps_piv: float = 1e-9):
+                 algo: int = _abi.ALGO_AUTO, eps_feas: float = 1e-9, eps_piv: float = -1.0,
+                 pivot_rule: int = _abi.PIVOT_ABSOLUTE):
         A = problem.GetConstraintsMatrix()
         m, n = A.shape
         if m > n:
@@ -170,8 +175,42 @@ class EnumerationSolver:
         self._problem = problem                      # reference copies (SimplexSolover.h:12,285); arrays are not mutated here
         self._devices = None if devices is None else [int(d) for d in devices]
         self._algo = int(algo)
-        self._eps = (float(eps_feas), float(eps_piv))
+        self._eps = (float(eps_feas), float(eps_piv))      # eps_piv < 0: the rule's default (1e-9 absolute, m*2^-52 relative)
+        self._rule = int(pivot_rule)
         self._res: Optional[_abi.Result] = None
+        self._handles = None                         # enumgpu_handle per device, created at the first solve, kept
+
+    # -- handles: stream, events, pinned staging, device buffers live as long as the solver (include/enumgpu.h) --
+    def _get_handles(self):
+        if self._handles is None:
+            hs = []
+            try:
+                for d in (self._devices if self._devices else [-1]):
+                    h = C.c_void_p()
+                    _check(lib().enumgpu_create(int(d), C.byref(h)))
+                    hs.append(h)
+            except BaseException:
+                for h in hs:
+                    lib().enumgpu_destroy(h)
+                raise
+            self._handles = hs
+        return self._handles
+
+    def close(self):
+        if self._handles:
+            for h in self._handles:
+                lib().enumgpu_destroy(h)
+        self._handles = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:            # interpreter shutdown
+            pass
+
+    def _options(self, rank_begin=0, rank_end=0, shard_index=0, shard_count=0):
+        return _abi.Options(self._eps[0], self._eps[1], rank_begin, rank_end, 0, self._algo, None, None,
+                            shard_index, shard_count, self._rule, 0)
 
     # -- the reference call shape ------------------------------------------
     def solve(self, rank_begin: int = 0, rank_end: int = 0) -> np.ndarray:
@@ -192,12 +231,13 @@ class EnumerationSolver:
         p = self._problem
         A, b, c = p.GetConstraintsMatrix(), p.GetRightHandSide(), p.GetObjectiveCoefficients()
         ps = _problem_struct(A, b, c, p.IsMaximization())
-        nd = 0 if self._devices is None else len(self._devices)
-        dev = (C.c_int32 * max(nd, 1))(*(self._devices or [0]))
-        o = _abi.Options(self._eps[0], self._eps[1], rank_begin, rank_end, nd, self._algo,
-                         C.cast(dev, C.POINTER(C.c_int32)) if nd else None, None, shard_index, shard_count)
+        o = self._options(rank_begin, rank_end, shard_index, shard_count)
         res = _abi.Result()
-        rc = lib().enumgpu_solve(C.byref(ps), C.byref(o), C.byref(res))
+        if lib().enumgpu_device_count() < 1:          # no device: let the library say so (no CPU fallback)
+            _check(lib().enumgpu_solve(C.byref(ps), C.byref(o), C.byref(res)))
+        hs = self._get_handles()
+        arr = (C.c_void_p * len(hs))(*[h.value for h in hs])
+        rc = lib().enumgpu_solve_hv(arr, len(hs), C.byref(ps), C.byref(o), C.byref(res))
         _check(rc)
         self._res = res
         return res
@@ -208,7 +248,7 @@ class EnumerationSolver:
         struct of the same enumeration is kept (feasibleCount() is the full count)."""
         p = self._problem
         ps = _problem_struct(p.GetConstraintsMatrix(), p.GetRightHandSide(), p.GetObjectiveCoefficients(), p.IsMaximization())
-        o = _abi.Options(self._eps[0], self._eps[1], 0, 0, 0, self._algo, None, None, 0, 0)
+        o = self._options()
         ranks = np.zeros(max(int(capacity), 1), dtype=np.uint64)
         n_listed = C.c_uint64()
         res = _abi.Result()
@@ -227,7 +267,7 @@ class EnumerationSolver:
         k = ranks.size
         xB = np.zeros((k, m)); z = np.zeros(k); cls = np.zeros(k, dtype=np.int32)
         ps = _problem_struct(A, p.GetRightHandSide(), p.GetObjectiveCoefficients(), p.IsMaximization())
-        o = _abi.Options(self._eps[0], self._eps[1], 0, 0, 0, self._algo, None, None, 0, 0)
+        o = self._options()
         _check(lib().enumgpu_eval_ranks(C.byref(ps), C.byref(o), ranks.ctypes.data_as(C.POINTER(C.c_uint64)), k,
                                         xB.ctypes.data_as(C.POINTER(C.c_double)), z.ctypes.data_as(C.POINTER(C.c_double)),
                                         cls.ctypes.data_as(C.POINTER(C.c_int32))))

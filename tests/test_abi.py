@@ -48,7 +48,7 @@ def test_struct_layouts_match_header(tmp_path):
 
 def test_version_and_binomials(oracle):
     L = sm.lib()
-    assert L.enumgpu_version() == 100
+    assert L.enumgpu_version() == 200
     assert L.enumgpu_binomial(5, 2) == 10
     assert L.enumgpu_binomial(24, 8) == 735471
     assert L.enumgpu_binomial(30, 10) == 30045015

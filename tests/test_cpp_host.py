@@ -28,7 +28,9 @@ def test_adapter_links_only_the_c_abi(built):
     """The demo's undefined enumgpu symbols are all declared in include/enumgpu.h."""
     syms = subprocess.check_output(["nm", "-u", os.path.join(built, "enum_demo")], text=True)
     used = sorted({l.split()[-1].split("@")[0] for l in syms.splitlines() if "enumgpu_" in l})
-    assert used == ["enumgpu_eval_basis", "enumgpu_last_error", "enumgpu_solve"]
+    assert used == ["enumgpu_create", "enumgpu_destroy", "enumgpu_eval_basis", "enumgpu_last_error", "enumgpu_solve_hv"]
+    header = open(os.path.join(ROOT, "include", "enumgpu.h")).read()
+    assert all(name + "(" in header for name in used)
 
 
 @pytest.mark.gpu
