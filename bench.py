@@ -6,20 +6,23 @@
 
 A *step* is one complete enumeration of all C(n, m) bases of one synthetic dense
 LP (default: BASELINE.json's roofline headline, m=12, n=40 -> 5 586 853 480
-bases).  With N > 1 (launched by torchrun, one process per GPU) the rank space
-is cut into N contiguous shards — strong scaling: the job is the same LP — and
-every step ends with one NCCL all_gather of the 256-byte partial records.
+bases).  With N > 1 (launched by torchrun, one process per GPU) rank r takes the
+interleaved cost-weighted windows r, r+N, ... of the rank space — strong
+scaling: the job is the same LP — and every step ends with one NCCL all_gather
+of the 256-byte partial records.
 
 Printed JSON line (rank 0):
-  value     bases/s, inputs resident in HBM, K steps bracketed by
-            barrier + cuda synchronize, max over ranks
+  value     bases/s, inputs resident in HBM; K steps inside a barrier +
+            cuda synchronize bracket, each timed with CUDA events on the
+            launching stream (launch + all-gather), max over ranks per step;
+            best and median per step are reported next to the mean
   e2e       same metric through the public host-buffer call
             (EnumerationSolver -> enumgpu_solve: H2D of A,b,c + kernels + D2H)
   roofline  FP64-pipe roofline of the enumeration kernel: algorithmic flops
             F(m) = 2/3 m^3 + 3/2 m^2 + 5/6 m per basis x bases per
-            launch / CUDA-event time of the launch; peak = in-run DFMA probe
-            (MEASURED_PEAKS.json carries no FP64 figure) next to the nominal
-            148 SM x 64 lanes x 2 x f_max
+            launch / CUDA-event time of the launch; peak = max(in-run DFMA
+            probe, nominal 148 SM x 64 lanes x 2 x f_max) (MEASURED_PEAKS.json
+            carries no FP64 figure)
   cpu_baseline  the CPU oracle on this box's host cores on a bounded sample
 
 --impl reference times the CPU arm only (the reference's EnumerationSolver is
@@ -185,9 +188,8 @@ def main():
     A, b, c, mx = lpgen.dense_lp(m, n, args.seed)
     workload = f"dense canonical LP m={m} n={n} seed={args.seed}: full enumeration of C({n},{m})={total} bases"
     config = {"workload": workload, "m": m, "n": n, "seed": args.seed, "bases_per_step": total,
-              "sharding": f"{world} shards of interleaved contiguous rank windows" if world > 1 else "single GPU",
-              "l2": "inputs are 4.3 KB staged once per CTA in shared memory; compute-bound, L2 state "
-                    "irrelevant; a 160 MB buffer (L2 is 126 MB) is rewritten between timed steps anyway"}
+              "sharding": f"{world} shards of interleaved cost-weighted windows" if world > 1 else "single GPU",
+              "l2": "inputs are (m*n+m+n)*8 bytes staged in shared memory; compute-bound, L2 state irrelevant"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -234,32 +236,34 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     algo = {"auto": _abi.ALGO_AUTO, "independent": _abi.ALGO_INDEPENDENT, "shared": _abi.ALGO_SHARED}[args.algo]
 
-    # this rank's shard (strong scaling: same LP): the interleaved rank windows
-    # rank, rank+world, ... of the whole space (enumgpu_options.shard_index/count)
+    # this rank's shard (strong scaling: same LP): the interleaved windows rank, rank+world, ... of the
+    # whole space (enumgpu_options.shard_index/count)
     from simplexmethod_b200 import dist as edist
-    lo, hi = 0, total
 
     # inputs resident in HBM
     dA = torch.from_numpy(np.ascontiguousarray(A.T)).to(dev)
     db, dc = torch.from_numpy(b).to(dev), torch.from_numpy(c).to(dev)
     scale = float(np.abs(A).max())
     pd = _abi.Problem(m, n, m, int(mx), dA.data_ptr(), db.data_ptr(), dc.data_ptr())
-    stream = torch.cuda.current_stream()
-    opt = _abi.Options(-1.0, -1.0, lo, hi, 0, algo, None, stream.cuda_stream, rank if world > 1 else 0, world if world > 1 else 0)
     part = torch.zeros(256, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(world * 256, dtype=torch.uint8, device=dev)
     flush = torch.empty(160 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB of L2
     nl = C.c_int32()
+    handle = C.c_void_p()
+    if L.enumgpu_create(local_rank, C.byref(handle)) != 0:
+        raise RuntimeError(sm.last_error())
+    # everything of a step — flush, events, the enumeration launch, the all-gather — goes to ONE stream: the handle's,
+    # made torch's current stream (torch.cuda.Event only sees the stream it is recorded on)
+    stream = torch.cuda.ExternalStream(L.enumgpu_handle_stream(handle), device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(stream)
+    opt = _abi.Options(-1.0, -1.0, 0, total, 0, algo, None, stream.cuda_stream, rank if world > 1 else 0, world if world > 1 else 0)
 
-    def step_device():
-        flush.fill_(1)                              # L2 flush between steps (126 MB L2)
-        rc = L.enumgpu_enqueue_device(C.byref(pd), scale, C.byref(opt), part.data_ptr(), C.byref(nl))
+    def enqueue_step():
+        rc = L.enumgpu_enqueue_h(handle, C.byref(pd), scale, C.byref(opt), part.data_ptr(), C.byref(nl))
         if rc != 0:
             raise RuntimeError(sm.last_error())
         edist.all_gather_records(part, gathered, world)
-
-    def merged_result():
-        return edist.merge_records(gathered.cpu().numpy().tobytes(), world)
 
     def barrier():
         if world > 1:
@@ -274,85 +278,106 @@ def main():
         return float(t.item())
 
     # ---- device-resident throughput -------------------------------------
+    # A step = [L2 flush, untimed] + [enumeration launch + all-gather of the records, timed with CUDA events on the
+    # launching stream].  The flush sits between the timed brackets: the path's working set is 4 KB of inputs held
+    # in shared memory, so the flush changes nothing measurable, but the rule asks for it and it must not be billed
+    # to the enumeration (at 8 GPUs the 160 MB fill was 0.65 % of a step).
     for _ in range(args.warmup):
-        step_device()
+        flush.fill_(1)
+        enqueue_step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(1)
         ev[i][0].record(stream)
-        rc = L.enumgpu_enqueue_device(C.byref(pd), scale, C.byref(opt), part.data_ptr(), C.byref(nl))
+        rc = L.enumgpu_enqueue_h(handle, C.byref(pd), scale, C.byref(opt), part.data_ptr(), C.byref(nl))
         if rc != 0:
             raise RuntimeError(sm.last_error())
         ev[i][1].record(stream)
         edist.all_gather_records(part, gathered, world)
+        ev[i][2].record(stream)
     barrier()
-    wall = max_over_ranks(time.perf_counter() - t0)
+    wall_incl_flush = max_over_ranks(time.perf_counter() - t0)
     launches_per_step = nl.value                     # kernels of libenumgpu per step (the L2-flush fill and the
-                                                     # 256-byte copy / NCCL all-gather are torch's and not counted)
-    kern_ms = [a.elapsed_time(bb) for a, bb in ev]   # this rank's enumeration launches (CUDA events, same stream)
+                                                     # NCCL all-gather / 256-byte copy are torch's and not counted)
+    kern_ms = [e[0].elapsed_time(e[1]) for e in ev]  # this rank's enumeration launches (CUDA events, same stream)
+    step_ms = [e[0].elapsed_time(e[2]) for e in ev]  # launch + all-gather: the timed step
+    # a step ends when its all-gather has delivered every rank's record: per step, the max over ranks
+    if world > 1:
+        t = torch.tensor(step_ms, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = t.cpu().tolist()
     kern_ms_own = float(np.mean(kern_ms))
-    kern_ms_mean = max_over_ranks(kern_ms_own)
+    kern_ms_max = max_over_ranks(kern_ms_own)
+    timed_s = 1e-3 * float(np.sum(step_ms))
     own_bases = _abi.Partial.from_buffer_copy(part.cpu().numpy().tobytes()).n_bases
-    res = merged_result()
-    value = total * args.steps / wall
+    res = edist.merge_records(gathered.cpu().numpy().tobytes(), world)
+    value = total * args.steps / timed_s
 
     # ---- end to end through the public host-buffer API ------------------
+    # N = 1: EnumerationSolver(canonical).enumerate() -> enumgpu_solve_hv (pack into pinned memory, H2D of A|b|c,
+    # one kernel, D2H of the 256-byte record, synchronise).  N > 1: dist.ShardedEnumeration.solve(), the same per
+    # rank plus the device-side all-gather and one D2H of the gathered records.
     can = sm.Canonical(A, b, c, list(range(m)), minimize=not mx)
-    solver = sm.EnumerationSolver(can, algo=algo)
-    pinned = torch.zeros(6, dtype=torch.float64).pin_memory()
-    g6 = torch.zeros(world * 6, dtype=torch.float64, device=dev)
-
-    def step_e2e():
-        r = solver.enumerate(rank_begin=lo, rank_end=hi, shard_index=rank if world > 1 else 0,
-                             shard_count=world if world > 1 else 0)       # H2D(A,b,c,binom) + kernels + D2H(256 B)
-        if world > 1:
-            pinned[0] = r.key; pinned[1] = float(r.best_rank); pinned[2] = r.n_singular
-            pinned[3] = r.n_infeasible; pinned[4] = r.n_feasible; pinned[5] = r.objective
-            dist.all_gather_into_tensor(g6, pinned.to(dev, non_blocking=True))
-            return g6.cpu()
-        return r
-
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+    if world == 1:
+        solver = sm.EnumerationSolver(can, algo=algo)
+        step_e2e = lambda: solver.enumerate()
+        h2d, d2h = (m * n + m + n) * 8, 256
+    else:
+        sharded = edist.ShardedEnumeration(local_rank, rank, world, algo)
+        step_e2e = lambda: sharded.solve(A, b, c, mx)
+        h2d, d2h = (m * n + m + n) * 8, 256 * world
+    for _ in range(max(2, args.warmup)):
+        r_e2e = step_e2e()
     barrier()
-    t0 = time.perf_counter()
+    e2e_times = []
     for _ in range(args.steps):
-        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        r_e2e = step_e2e()
+        e2e_times.append(time.perf_counter() - t0)
     barrier()
-    e2e_wall = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = total * args.steps / e2e_wall
-    h2d = (m * n + m + n) * 8 + 8 * 65 * 17
+    if world > 1:
+        t = torch.tensor(e2e_times, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_times = t.cpu().tolist()
+    e2e_s = float(np.sum(e2e_times))
+    e2e_value = total * args.steps / e2e_s
+    assert (r_e2e.best_rank, r_e2e.n_feasible, r_e2e.n_singular) == (res.best_rank, res.n_feasible, res.n_singular)
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
         dist.barrier()
     if rank != 0:
+        L.enumgpu_destroy(handle)
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- roofline of the enumeration launch ------------------------------
     F = algo_flops_per_basis(m)
-    probe = L.enumgpu_fp64_peak_tflops(3)
+    probe_detail = (C.c_double * 2)(0.0, 0.0)
+    probe = L.enumgpu_fp64_peak_detail(3, probe_detail)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    sm_max = float((clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0))
     nominal = 148 * 64 * 2 * sm_max * 1e6 / 1e12
+    peak = max(probe, nominal)                  # the larger of the two: never flatter the kernel with a low probe
     shard = own_bases                           # bases this rank's launch visited
     achieved = shard * F / (kern_ms_own * 1e-3) / 1e12
+    kernel_name = "k_shared" if res.algo_used == _abi.ALGO_SHARED else "k_independent"
     # the "one LU per basis" kernel on a bounded sample, for the same roofline: what the FP64 pipe does
     # when nothing is shared or pruned (ENUMGPU_ALGO_INDEPENDENT, same arithmetic, same results)
     indep = None
-    if world == 1:
+    if world == 1 and res.algo_used == _abi.ALGO_SHARED:
         sample = min(total, 200_000_000)
         opt_i = _abi.Options(-1.0, -1.0, 0, sample, 0, _abi.ALGO_INDEPENDENT, None, stream.cuda_stream)
         res_i = _abi.Result()
@@ -361,40 +386,73 @@ def main():
                 raise RuntimeError(sm.last_error())
         ach_i = sample * F / (res_i.kernel_ms * 1e-3) / 1e12
         indep = {"kernel": "k_independent", "sample_ranks": sample, "launch_ms": res_i.kernel_ms,
-                 "bases_per_s": sample / (res_i.kernel_ms * 1e-3), "achieved": ach_i,
-                 "frac": ach_i / probe if probe > 0 else None}
-    # executed (not algorithmic) work of k_shared, from the ncu capture under profiles/
-    executed = None
-    if res.algo_used == _abi.ALGO_SHARED and (m, n) == (12, 40):
-        fpb = 2 * 39.27 + 8.79 + 0.00           # DFMA x2 + DMUL + DADD thread-instructions per basis
-        ex = shard * fpb / (kern_ms_own * 1e-3) / 1e12
-        executed = {"flops_per_basis": fpb, "tflops": ex, "frac_of_peak": ex / probe if probe > 0 else None,
-                    "warp_instructions_per_basis": 6.54, "fp64_pipe_busy_pct": 31.4, "issue_slots_busy_pct": 59.5,
-                    "source": "profiles/r1_k_shared_m12n40_ncu_key_metrics.csv (ncu --set full, full-range launch)"}
-    roofline = {"bound": "fp64", "achieved": achieved, "peak": probe, "unit": "TFLOP/s",
-                "frac": achieved / probe if probe > 0 else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one k_shared<12> launch over the full
-                # C(40,12) range, from the ncu --set full capture under profiles/ (r1_k_shared_m12n40_ncu_key_metrics.csv)
-                "traffic": 1389056 if (m, n, world) == (12, 40, 1) and res.algo_used == _abi.ALGO_SHARED else None,
-                "traffic_unit": "bytes per launch (algorithmic input: 13 KB; the rest is instruction fetch, tables, spill write-back)",
-                "peak_source": "in-run register-resident DFMA-chain probe (enumgpu_fp64_peak_tflops); "
+                 "bases_per_s": sample / (res_i.kernel_ms * 1e-3), "achieved": ach_i, "frac": ach_i / peak}
+    # executed (not algorithmic) work and DRAM traffic of the kernel: ONLY from an ncu capture of this very kernel —
+    # the key-metrics file under profiles/ is used iff its recorded launch time is within 3 % of the launch time
+    # measured in this run (same code, same configuration); otherwise these fields are null, never stale constants
+    executed, traffic, profile_note = None, None, None
+    prof = os.path.join(ROOT, "profiles", f"r2_{kernel_name}_m{m}n{n}_ncu_key_metrics.csv")
+    if world == 1 and os.path.exists(prof):
+        kv = {}
+        for line in open(prof):
+            f = line.rstrip("\n").split(",")
+            if len(f) >= 3:
+                try:
+                    kv[f[0]] = float(f[2])
+                except ValueError:
+                    pass
+        t_prof = kv.get("gpu__time_duration.sum")
+        if t_prof and abs(t_prof - kern_ms_own) <= 0.03 * kern_ms_own:
+            fpb = kv.get("derived_executed_flops_per_basis")
+            if fpb:
+                ex = shard * fpb / (kern_ms_own * 1e-3) / 1e12
+                executed = {"flops_per_basis": fpb, "tflops": ex, "frac_of_peak": ex / peak,
+                            "warp_instructions_per_basis": kv.get("derived_warp_inst_per_basis"),
+                            "fp64_pipe_busy_pct": kv.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                            "issue_slots_busy_pct": kv.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                            "from_profile": os.path.relpath(prof, ROOT), "profile_launch_ms": t_prof}
+            rd, wr = kv.get("dram__bytes_read.sum"), kv.get("dram__bytes_write.sum")
+            if rd is not None and wr is not None:
+                traffic = int(round((rd + wr) * 1e3))          # the file records Kbyte
+        else:
+            profile_note = (f"{os.path.relpath(prof, ROOT)} records a {t_prof} ms launch, this run measured {kern_ms_own:.3f} ms: "
+                            "more than 3 % apart, so executed/traffic are not quoted")
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic,
+                "traffic_unit": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of the ncu capture named in "
+                                "executed.from_profile (algorithmic input: (m*n+m+n)*8 bytes; the rest is instruction fetch, "
+                                "tables, spill write-back); null when no capture matches this build",
+                "peak_source": "max(in-run register-resident DFMA-chain probe, nominal 148 SM x 64 lanes x 2 x f_max); "
                                "MEASURED_PEAKS.json has no FP64 figure",
-                "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
-                "flops_per_basis": F, "bases_per_launch": shard, "launch_ms": kern_ms_own, "launch_ms_max_over_ranks": kern_ms_mean,
-                "kernel": "k_shared" if res.algo_used == _abi.ALGO_SHARED else "k_independent",
-                "executed": executed, "per_basis_lu_kernel": indep,
+                "peak_probe": probe, "peak_nominal": nominal,
+                "peak_probe_detail": {"dfma_warp_instr_per_sm_cycle": probe_detail[0], "sm_mhz_during_probe": probe_detail[1],
+                                      "note": "the pipe issues at most 2 DFMA warp-instructions per SM cycle; probe = that rate x 32 lanes "
+                                              "x 2 flops x 148 SMs x the clock the chip holds under full FP64 load"},
+                "flops_per_basis": F, "bases_per_launch": shard, "launch_ms": kern_ms_own,
+                "launch_ms_best": float(np.min(kern_ms)), "launch_ms_median": float(np.median(kern_ms)),
+                "launch_ms_max_over_ranks": kern_ms_max, "kernel": kernel_name,
+                "executed": executed, "profile_note": profile_note, "per_basis_lu_kernel": indep,
                 "note": "achieved/frac are ALGORITHMIC flops (one dgesv + dot per basis, SURVEY 8d); k_shared shares the "
                         "first m-4 elimination steps between bases and prunes the back substitution, so frac > 1 is "
                         "expected: 'executed' is what the FP64 pipe really did, 'per_basis_lu_kernel' the kernel "
                         "that does one full LU per basis (DESIGN.md 5-6)"}
 
+    config["l2"] = ("inputs are (m*n+m+n)*8 bytes staged in shared memory; compute-bound, L2 state irrelevant; a 160 MB "
+                    "buffer (L2 is 126 MB) is rewritten between the timed steps, outside the CUDA-event brackets")
+    config["timing"] = ("per step: CUDA events on the launching stream around [enumeration launch + all-gather of the 256-byte "
+                        "records]; per step the max over ranks; value = bases x steps / sum of the steps")
     out = {
         "metric": "bases evaluated per second", "value": value, "unit": "bases/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * timed_s / args.steps,
+        "ms_per_step_best": float(np.min(step_ms)), "ms_per_step_median": float(np.median(step_ms)),
+        "wall_ms_per_step_incl_flush": 1e3 * wall_incl_flush / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 256,
-                "ms_per_step": 1e3 * e2e_wall / args.steps},
+        "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "ms_per_step_best": 1e3 * float(np.min(e2e_times)),
+                "ms_per_step_median": 1e3 * float(np.median(e2e_times)),
+                "api": "EnumerationSolver.enumerate -> enumgpu_solve_hv" if world == 1 else
+                       "dist.ShardedEnumeration.solve -> enumgpu_enqueue_h + NCCL all-gather"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks, "roofline": roofline,
         "result": {"status": res.status, "best_rank": res.best_rank, "basis": list(res.basis)[:m],
@@ -407,6 +465,7 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": "bases/s", "cores": threads, "kind": "port",
                                "sample": desc + "; Eigen-free oracle port (the reference path is a stub and Eigen is absent)"}
     print(json.dumps(out))
+    L.enumgpu_destroy(handle)
     if world > 1:
         dist.destroy_process_group()
 

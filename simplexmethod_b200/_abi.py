@@ -95,6 +95,7 @@ SYMBOLS = {
     "enumgpu_merge_partial": (None, [C.POINTER(Partial), C.POINTER(Partial)]),
     "enumgpu_shard_begin": (C.c_uint64, [C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32]),
     "enumgpu_fp64_peak_tflops": (C.c_double, [C.c_int32]),
+    "enumgpu_fp64_peak_detail": (C.c_double, [C.c_int32, C.POINTER(C.c_double)]),
     "enumgpu_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
     "enumgpu_destroy": (None, [C.c_void_p]),
     "enumgpu_solve_h": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.POINTER(Options), C.POINTER(Result)]),

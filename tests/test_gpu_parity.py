@@ -561,13 +561,19 @@ def test_enqueue_h_back_to_back_on_one_stream(gpu_lib, oracle):
         dA = torch.from_numpy(np.ascontiguousarray(A.T)).cuda()
         db, dc = torch.from_numpy(b).cuda(), torch.from_numpy(c).cuda()
         pd = _abi.Problem(8, 20, 8, 0, dA.data_ptr(), db.data_ptr(), dc.data_ptr())
-        opt = _abi.Options(-1, -1, 0, 0, 0, 0, None, torch.cuda.current_stream().cuda_stream)
         bufs = [torch.zeros(256, dtype=torch.uint8, device="cuda") for _ in range(6)]
+        torch.cuda.synchronize()
         nl = C.c_int32()
-        for buf in bufs:
+        side = torch.cuda.Stream()                        # a caller-owned stream: every enqueue of this handle goes there
+        opt = _abi.Options(-1, -1, 0, 0, 0, 0, None, side.cuda_stream)
+        for buf in bufs[:3]:
             assert gpu_lib.enumgpu_enqueue_h(h, C.byref(pd), float(np.abs(A).max()), C.byref(opt), buf.data_ptr(), C.byref(nl)) == 0
             assert nl.value == 1
-        torch.cuda.synchronize()
+        side.synchronize()
+        opt.stream = None                                 # NULL: the handle's own stream
+        for buf in bufs[3:]:
+            assert gpu_lib.enumgpu_enqueue_h(h, C.byref(pd), float(np.abs(A).max()), C.byref(opt), buf.data_ptr(), C.byref(nl)) == 0
+        torch.cuda.ExternalStream(gpu_lib.enumgpu_handle_stream(h)).synchronize()
         for buf in bufs:
             rec = _abi.Partial.from_buffer_copy(buf.cpu().numpy().tobytes())
             res = _abi.Result()

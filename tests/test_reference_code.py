@@ -293,6 +293,35 @@ def test_reference_enumeration_vs_oracle_headline_window(oracle):
         _compare(ref, res, 12)
 
 
+def test_headline_singular_bases_reference_vs_both_rules(oracle):
+    """The 9 bases of dense(12,40,1) that the default ABSOLUTE pivot rule rejects (|pivot| <= 1e-9 max|A|; their
+    condition numbers are 3e10..3e11): the ONLY ranks of the headline LP where the rule can disagree with the
+    reference's Solver::computeBFS test, FullPivLU::isInvertible (SimplexSolover.h:124-126, relative threshold
+    eps*m).  Asked one by one: the reference's own code says NOT singular -> infeasible (x_B ~ -1e9); so does
+    ENUMGPU_PIVOT_RELATIVE; the absolute rule says singular.  n_feasible and the optimum are the same under
+    both; only 9 bases move between n_singular and n_infeasible."""
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "dense_12_40_seed1.json")))
+    ranks = g["singular_ranks"]
+    assert len(ranks) == g["n_singular"] == 9
+    A, b, c, mx = lpgen.dense_lp(12, 40, 1)
+    import ctypes as C
+    S = (C.c_int32 * 12)()
+    for r in ranks:
+        assert sm.lib().enumgpu_unrank(40, 12, r, S) == 0
+        basis = list(S)
+        assert 1e10 < np.linalg.cond(A[:, basis]) < 1e12
+        assert oracle.eval_basis(A, b, c, mx, basis)[0] == oracle.SINGULAR                       # absolute rule
+        st_rel, x_rel, _ = oracle.eval_basis(A, b, c, mx, basis, pivot_rule=1)                   # Eigen-like rule
+        assert st_rel == oracle.INFEASIBLE and min(x_rel) < -1e8
+        ref, st_ref = R.enumerate_bases(A, b, c, mx, want_status=True, rank_begin=r, rank_end=r + 1)
+        assert st_ref.tolist() == [oracle.INFEASIBLE] and (ref.n_singular, ref.n_infeasible) == (0, 1)
+        # a 1-rank window of the oracle enumeration under each rule says the same as eval_basis
+        for rule, want in ((0, (1, 0)), (1, (0, 1))):
+            o, _ = oracle.solve(A, b, c, mx, rank_begin=r, rank_end=r + 1, pivot_rule=rule)
+            assert (o.n_singular, o.n_infeasible) == want
+
+
 # ---- the reference's simplex Solver vs the enumeration optimum (README.md:42) -------------------
 
 @pytest.mark.parametrize("case", ["lab_symmetric", "main_cpp", "dense1", "dense2", "dense3", "dense_12_40"])
