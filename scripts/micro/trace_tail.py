@@ -16,13 +16,18 @@ if len(sys.argv) > 5 and sys.argv[5] == "child":
     for i in range(3):
         r = s.enumerate(0, 0, shard_index=si, shard_count=sc)
     print("KERNEL_MS", r.kernel_ms, flush=True)
-    buf = (C.c_ulonglong * (3 * 16 * 148))()
-    assert sm.lib().enumgpu_trace_read(buf, len(buf)) == 0
+    buf = (C.c_ulonglong * (4 * 16 * 148))()
+    L = C.CDLL(_lib.LIB_PATH)
+    assert L.enumgpu_trace_read(buf, len(buf)) == 0
+    done = (C.c_ulonglong * 2)()
+    L.enumgpu_trace_done(done)
+    print("DONE", done[1])
     for w in range(16 * 148):
-        print("T", w // 16, w % 16, buf[3 * w], buf[3 * w + 1], buf[3 * w + 2])
+        if buf[4 * w + 1]:
+            print("T", w // 16, w % 16, buf[4 * w], buf[4 * w + 1], buf[4 * w + 2], buf[4 * w + 3])
     sys.exit(0)
 out = subprocess.run([sys.executable, __file__] + sys.argv[1:5] + ["child"], capture_output=True, text=True).stdout
-rows, ms = [], None
+rows, ms, done = [], None, 0
 for line in out.splitlines():
     if line.startswith("LAUNCH"):
         rows = []
@@ -30,10 +35,15 @@ for line in out.splitlines():
         rows.append([int(v) for v in line.split()[1:]])
     elif line.startswith("KERNEL_MS"):
         ms = float(line.split()[1])
+    elif line.startswith("DONE"):
+        done = int(line.split()[1])
 import numpy as np
 a = np.array(rows, dtype=np.int64)
-t0, t1, units = a[:, 2], a[:, 3], a[:, 4]
-g0 = t0.min()
+t0, t1, units, entry = a[:, 2], a[:, 3], a[:, 4], a[:, 5]
+g0 = entry.min()
+print(f"kernel entry (first CTA) = 0;  CTA entries spread {(entry.max() - g0) / 1e3:.1f} us;  prologue (entry -> unit loop): "
+      f"mean {(t0 - entry).mean() / 1e3:.1f} us max {(t0 - entry).max() / 1e3:.1f} us;  record written {(done - g0) / 1e3:.1f} us "
+      f"({(done - t1.max()) / 1e3:.1f} us after the last warp stopped)")
 end = (t1 - g0) / 1e6
 start = (t0 - g0) / 1e6
 print(f"warps {len(a)}  kernel_ms(event) {ms:.3f}  span first-start..last-end {end.max():.3f} ms")

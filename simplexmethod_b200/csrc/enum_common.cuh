@@ -215,7 +215,9 @@ __device__ inline int eval_basis_generic(const double* A, int lda, const double*
 // of shared memory that the block no longer needs (8-byte aligned).  blockDim.x: a multiple of 32, <= 1024.
 constexpr int kFinalizeScratch = 8 * (kMaxM * (kMaxM + 1) + kMaxM) + 4 * kMaxM + 32 * 40 + 16;
 
-__device__ __forceinline__ void finalize_if_last(const LaunchParams& prm, unsigned char* scratch)
+// `sbinom`: the block's shared-memory copy of the binomial table (row stride kBinomCols), still intact — unranking the
+// winner from global memory is a chain of ~n+m dependent L2 reads, 8 us of the 20 the finalize took.
+__device__ __forceinline__ void finalize_if_last(const LaunchParams& prm, unsigned char* scratch, const uint64_t* sbinom)
 {
     __shared__ int s_is_last;
     if (threadIdx.x == 0) {
@@ -271,7 +273,7 @@ __device__ __forceinline__ void finalize_if_last(const LaunchParams& prm, unsign
         for (int i = 0; i < kMaxM; ++i) { r->x_B[i] = 0.0; r->basis[i] = 0; }
         r->objective = __longlong_as_double(0x7ff8000000000000LL);
         s_best[0] = rank;
-        if (rank != ~0ull) unrank_lex(prm.binom, prm.n, prm.m, rank, s_S);
+        if (rank != ~0ull) unrank_lex(sbinom, prm.n, prm.m, rank, s_S);
         prm.ctrl->unit_counter = 0ull;                     // ready for the next enqueue on this control block
         prm.ctrl->ticket = 0u;
     }

@@ -158,7 +158,7 @@ k_independent(const LaunchParams prm, BlockPartial* __restrict__ partials)
         }
     }
     block_reduce<kIndepThreads>(best_key, best_rank, ns, ni, nf, partials + blockIdx.x);
-    finalize_if_last(prm, smem_raw);      // staged A, b, c are dead: every thread has passed block_reduce's barrier
+    finalize_if_last(prm, reinterpret_cast<unsigned char*>(sbin + kBinomRows * kBinomCols), sbin);
 }
 
 // Run-time m (local-memory arrays): m above the register-resident range, and every m under the
@@ -208,7 +208,7 @@ k_independent_generic(const LaunchParams prm, BlockPartial* __restrict__ partial
         }
     }
     block_reduce<kIndepThreads>(best_key, best_rank, ns, ni, nf, partials + blockIdx.x);
-    finalize_if_last(prm, smem_raw);
+    finalize_if_last(prm, reinterpret_cast<unsigned char*>(sbin + kBinomRows * kBinomCols), sbin);
 }
 
 }  // namespace enumgpu
