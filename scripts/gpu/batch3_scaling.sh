@@ -14,7 +14,7 @@ run() {  # name N extra-args...
   echo "$name N=$n rc=$? $(head -c 160 gpurun_out/r2s_${name}_n$n.json)"
 }
 for n in 1 2 4 8; do run m12n40 $n --steps 10 --warmup 3 --no-cpu-baseline; done
-for n in 1 2 4 8; do run m10n30 $n --m 10 --n 30 --steps 50 --warmup 5 --no-cpu-baseline; done
-run m8n24 1 --m 8 --n 24 --steps 50 --warmup 5 --no-cpu-baseline
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "multi_device" > gpurun_out/r2s_multi_device_pytest.log 2>&1; echo "multi-device pytest rc=$?" | tee -a gpurun_out/r2s_multi_device_pytest.log
+for n in 1 2 4 8; do run m10n30 $n --lp-m 10 --lp-n 30 --steps 50 --warmup 5 --no-cpu-baseline; done
+run m8n24 1 --lp-m 8 --lp-n 24 --steps 50 --warmup 5 --no-cpu-baseline
+timeout 600 python -m pytest tests/test_gpu_parity.py -v -k "multi_device" > gpurun_out/r2s_multi_device_pytest.log 2>&1; echo "multi-device pytest rc=$?" | tee -a gpurun_out/r2s_multi_device_pytest.log
 tail -3 gpurun_out/r2s_multi_device_pytest.log
