@@ -104,6 +104,8 @@ SYMBOLS = {
     "enumgpu_enqueue_h": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.c_double, C.POINTER(Options), C.c_void_p,
                                      C.POINTER(C.c_int32)]),
     "enumgpu_handle_stream": (C.c_void_p, [C.c_void_p]),
+    "enumgpu_enqueue_host_h": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.POINTER(Options), C.c_void_p, C.POINTER(C.c_int32)]),
+    "enumgpu_merge_records": (None, [C.c_void_p, C.c_int32, C.POINTER(Result)]),
     "enumgpu_selftest_rcp": (C.c_int, [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
 }
 

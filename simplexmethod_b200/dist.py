@@ -48,18 +48,16 @@ def interleaved_windows(total: int, rank: int, world: int, window: int, rank_beg
 class ShardedEnumeration:
     """The host-buffer solve of one process of a one-process-per-GPU job (the multi-process twin of
     ``EnumerationSolver.enumerate``): pack A|b|c into pinned memory, H2D, enumerate this rank's interleaved shard
-    (``enumgpu_enqueue_h`` on torch's current stream — one kernel launch), all-gather the 256-byte records on
-    the DEVICE (NCCL), one D2H copy of the gathered records into pinned memory, merge.  Every rank returns the
-    same result.  All buffers, the handle and the stream outlive the call."""
+    (``enumgpu_enqueue_host_h`` on the handle's stream — one copy, one kernel launch), all-gather the 256-byte
+    records on the DEVICE (NCCL), one D2H copy of the gathered records into pinned memory, merge
+    (``enumgpu_merge_records``).  Every rank returns the same result.  All buffers, the handle and the stream
+    outlive the call."""
 
     def __init__(self, device_index: int, rank: int, world: int, algo: int = _abi.ALGO_AUTO):
         import torch
         self._torch = torch
         self.rank, self.world, self.algo = int(rank), int(world), int(algo)
         self.dev = torch.device("cuda", device_index)
-        cap = _abi.MAX_M * _abi.MAX_N + _abi.MAX_M + _abi.MAX_N
-        self.h_in = torch.zeros(cap, dtype=torch.float64).pin_memory()
-        self.d_in = torch.zeros(cap, dtype=torch.float64, device=self.dev)
         self.part = torch.zeros(RECORD_BYTES, dtype=torch.uint8, device=self.dev)
         self.gathered = torch.zeros(world * RECORD_BYTES, dtype=torch.uint8, device=self.dev)
         self.h_gathered = torch.zeros(world * RECORD_BYTES, dtype=torch.uint8).pin_memory()
@@ -77,30 +75,25 @@ class ShardedEnumeration:
             self.handle = C.c_void_p()
 
     def solve(self, A, b, c, maximize: bool, rank_begin: int = 0, rank_end: int = 0) -> _abi.Result:
-        import numpy as np
+        """A: (m, n) float64 in column-major (Fortran) order, b, c: float64 vectors (what Canonical's getters return)."""
         torch = self._torch
         m, n = A.shape
-        k = m * n
-        hin = self.h_in.numpy()
-        hin[:k] = np.asarray(A, dtype=np.float64).reshape(-1, order="F")     # column-major, lda = m
-        hin[k:k + m] = b
-        hin[k + m:k + m + n] = c
-        scale = float(np.abs(hin[:k]).max())
-        self.h2d_bytes = (k + m + n) * 8
+        ps = _abi.Problem(m, n, A.strides[1] // 8 if n > 1 else m, int(bool(maximize)), A.ctypes.data, b.ctypes.data, c.ctypes.data)
+        self.h2d_bytes = (m * n + m + n) * 8
         stream = self.stream
+        sharded = self.world > 1
+        opt = _abi.Options(-1.0, -1.0, rank_begin, rank_end, 0, self.algo, None, stream.cuda_stream,
+                           self.rank if sharded else 0, self.world if sharded else 0)
+        # pack into pinned memory + H2D + the enumeration kernel, one C call, nothing synchronised
+        if lib().enumgpu_enqueue_host_h(self.handle, C.byref(ps), C.byref(opt), self.part.data_ptr(), None) != 0:
+            raise RuntimeError(lib().enumgpu_last_error().decode())
         with torch.cuda.stream(stream):
-            self.d_in[:k + m + n].copy_(self.h_in[:k + m + n], non_blocking=True)
-            base = self.d_in.data_ptr()
-            pd = _abi.Problem(m, n, m, int(bool(maximize)), base, base + 8 * k, base + 8 * (k + m))
-            sharded = self.world > 1
-            opt = _abi.Options(-1.0, -1.0, rank_begin, rank_end, 0, self.algo, None, stream.cuda_stream,
-                               self.rank if sharded else 0, self.world if sharded else 0)
-            if lib().enumgpu_enqueue_h(self.handle, C.byref(pd), scale, C.byref(opt), self.part.data_ptr(), None) != 0:
-                raise RuntimeError(lib().enumgpu_last_error().decode())
-            all_gather_records(self.part, self.gathered, self.world)
-            self.h_gathered.copy_(self.gathered, non_blocking=True)
+            all_gather_records(self.part, self.gathered, self.world)        # device side (NCCL)
+            self.h_gathered.copy_(self.gathered, non_blocking=True)         # one D2H copy into pinned memory
         stream.synchronize()
-        return merge_records(self.h_gathered.numpy().tobytes(), self.world)
+        res = _abi.Result()
+        lib().enumgpu_merge_records(self.h_gathered.data_ptr(), self.world, C.byref(res))
+        return res
 
 
 def merge_records(raw: bytes, world: int) -> _abi.Result:

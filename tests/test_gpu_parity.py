@@ -624,3 +624,21 @@ def test_eval_basis_any_size(gpu_lib, oracle):
     assert rep.IsFeasibleBasis() is False
     with pytest.raises(RuntimeError, match="Singular"):
         rep.GetBasicSolution()
+
+
+def test_sharded_enumeration_host_path_single_rank(gpu_lib, oracle):
+    """dist.ShardedEnumeration.solve (enumgpu_enqueue_host_h + gather + enumgpu_merge_records) with WORLD = 1:
+    the host-buffer path a one-process-per-GPU job runs on every rank (bench.py's e2e at N > 1), without NCCL."""
+    from simplexmethod_b200 import dist as edist
+    se = edist.ShardedEnumeration(0, 0, 1)
+    try:
+        for lp, m in ((lpgen.dense_lp(8, 24, 2), 8), (lpgen.small_degenerate_lp(), 7), (lpgen.dense_lp(6, 16, 21), 6)):
+            A, b, c, mx = lp
+            o, _ = oracle.solve(A, b, c, mx, n_threads=4)
+            for _ in range(2):
+                assert_same(se.solve(A, b, c, mx), o, m)
+        A, b, c, mx = lpgen.dense_lp(8, 24, 2)
+        o, _ = oracle.solve(A, b, c, mx, n_threads=4, rank_begin=1000, rank_end=500000)
+        assert_same(se.solve(A, b, c, mx, rank_begin=1000, rank_end=500000), o, 8)
+    finally:
+        se.close()
