@@ -253,9 +253,9 @@ def main():
     handle = C.c_void_p()
     if L.enumgpu_create(local_rank, C.byref(handle)) != 0:
         raise RuntimeError(sm.last_error())
-    # everything of a step — flush, events, the enumeration launch, the all-gather — goes to ONE stream: the handle's,
-    # made torch's current stream (torch.cuda.Event only sees the stream it is recorded on)
-    stream = torch.cuda.ExternalStream(L.enumgpu_handle_stream(handle), device=dev)
+    # everything of a step — flush, events, the enumeration launch, the all-gather — goes to ONE stream, torch's
+    # current one, handed to the library per call (torch.cuda.Event only sees the stream it is recorded on)
+    stream = torch.cuda.Stream(device=dev)
     torch.cuda.synchronize()
     torch.cuda.set_stream(stream)
     opt = _abi.Options(-1.0, -1.0, 0, total, 0, algo, None, stream.cuda_stream, rank if world > 1 else 0, world if world > 1 else 0)
@@ -394,14 +394,19 @@ def main():
     executed, traffic, profile_note = None, None, None
     prof = os.path.join(ROOT, "profiles", f"r2_{kernel_name}_m{m}n{n}_ncu_key_metrics.csv")
     if world == 1 and os.path.exists(prof):
-        kv = {}
+        kv, unit_of = {}, {}
         for line in open(prof):
             f = line.rstrip("\n").split(",")
             if len(f) >= 3:
                 try:
                     kv[f[0]] = float(f[2])
+                    unit_of[f[0]] = f[1]
                 except ValueError:
                     pass
+        to_ms = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+        to_bytes = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        if "gpu__time_duration.sum" in kv:
+            kv["gpu__time_duration.sum"] *= to_ms.get(unit_of["gpu__time_duration.sum"], 1.0)
         t_prof = kv.get("gpu__time_duration.sum")
         if t_prof and abs(t_prof - kern_ms_own) <= 0.03 * kern_ms_own:
             fpb = kv.get("derived_executed_flops_per_basis")
@@ -414,7 +419,8 @@ def main():
                             "from_profile": os.path.relpath(prof, ROOT), "profile_launch_ms": t_prof}
             rd, wr = kv.get("dram__bytes_read.sum"), kv.get("dram__bytes_write.sum")
             if rd is not None and wr is not None:
-                traffic = int(round((rd + wr) * 1e3))          # the file records Kbyte
+                traffic = int(round(rd * to_bytes.get(unit_of["dram__bytes_read.sum"], 1.0) +
+                                    wr * to_bytes.get(unit_of["dram__bytes_write.sum"], 1.0)))
         else:
             profile_note = (f"{os.path.relpath(prof, ROOT)} records a {t_prof} ms launch, this run measured {kern_ms_own:.3f} ms: "
                             "more than 3 % apart, so executed/traffic are not quoted")

@@ -64,13 +64,16 @@ class ShardedEnumeration:
         self.handle = C.c_void_p()
         if lib().enumgpu_create(device_index, C.byref(self.handle)) != 0:
             raise RuntimeError(lib().enumgpu_last_error().decode())
-        # copies, the enumeration launch and the all-gather are all ordered on the handle's own stream
-        self.stream = torch.cuda.ExternalStream(lib().enumgpu_handle_stream(self.handle), device=self.dev)
+        # copies, the enumeration launch and the all-gather are all ordered on ONE stream, owned by torch and handed to
+        # the library per call (options.stream): torch's allocators remember the streams their buffers were used on,
+        # so the stream must outlive the tensors — a stream owned by the handle would die with close()
+        self.stream = torch.cuda.Stream(device=self.dev)
         self.h2d_bytes = 0
         self.d2h_bytes = world * RECORD_BYTES
 
     def close(self):
         if self.handle:
+            self.stream.synchronize()
             lib().enumgpu_destroy(self.handle)
             self.handle = C.c_void_p()
 
