@@ -283,34 +283,43 @@ __device__ __forceinline__ void finalize_if_last(const LaunchParams& prm, unsign
         if (lane <= m)
             for (int r = 0; r < m; ++r) s_M[r * kLd + lane] = lane < m ? prm.A[r + (size_t)s_S[lane] * prm.lda] : prm.b[r];
         __syncwarp();
+        // (the warp spreads the independent elements of each step over its lanes; every element still receives
+        // the operations of eval_basis_generic in the same order — the serial version took 8 us of a launch)
         for (int k = 0; k < m; ++k) {
-            int p = k;                                       // first maximum of |M[r][k]|, r >= k (uniform)
-            double best = fabs(s_M[k * kLd + k]);
-            for (int r = k + 1; r < m; ++r) {
-                const double v = fabs(s_M[r * kLd + k]);
-                if (v > best) { best = v; p = r; }
+            // first maximum of |M[r][k]| over r >= k: lane r holds row r's candidate, a shuffle arg-max picks the
+            // largest value and, among equal ones, the lowest row (what the serial scan with '>' keeps)
+            double best = (lane >= k && lane < m) ? fabs(s_M[lane * kLd + k]) : -1.0;
+            int p = lane;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double v2 = __shfl_xor_sync(full, best, off);
+                const int p2 = __shfl_xor_sync(full, p, off);
+                if (v2 > best || (v2 == best && p2 < p)) { best = v2; p = p2; }
             }
-            __syncwarp();
             if (p != k && lane >= k && lane <= m) { const double t = s_M[k * kLd + lane]; s_M[k * kLd + lane] = s_M[p * kLd + lane]; s_M[p * kLd + lane] = t; }
             __syncwarp();
             const double rinv = __drcp_rn(s_M[k * kLd + k]);
             if (lane == 0) s_rinv[k] = rinv;
-            if (lane > k && lane <= m)
-                for (int r = k + 1; r < m; ++r)
-                    s_M[r * kLd + lane] = fnma(__dmul_rn(s_M[r * kLd + k], rinv), s_M[k * kLd + lane], s_M[r * kLd + lane]);
+            const int cols = m - k, n_el = (m - 1 - k) * cols;          // rows k+1..m-1, columns k+1..m
+            for (int e = lane; e < n_el; e += 32) {
+                const int r = k + 1 + e / cols, j = k + 1 + e % cols;
+                s_M[r * kLd + j] = fnma(__dmul_rn(s_M[r * kLd + k], rinv), s_M[k * kLd + j], s_M[r * kLd + j]);
+            }
             __syncwarp();
         }
-        if (lane == 0) {
-            enumgpu_partial* r = prm.record;
-            double z = 0.0;
-            for (int j = m - 1; j >= 0; --j) {
-                const double xj = __dmul_rn(s_M[j * kLd + m], s_rinv[j]);
-                for (int i = 0; i < j; ++i) s_M[i * kLd + m] = fnma(s_M[i * kLd + j], xj, s_M[i * kLd + m]);
+        enumgpu_partial* r = prm.record;
+        double z = 0.0;                                             // lane 0's
+        for (int j = m - 1; j >= 0; --j) {
+            const double xj = __dmul_rn(s_M[j * kLd + m], s_rinv[j]);      // the same value in every lane
+            __syncwarp();
+            if (lane < j) s_M[lane * kLd + m] = fnma(s_M[lane * kLd + j], xj, s_M[lane * kLd + m]);
+            if (lane == 0) {
                 z = __fma_rn(prm.c[s_S[j]], xj, z);
                 r->x_B[j] = xj; r->basis[j] = s_S[j];
             }
-            r->objective = z;
+            __syncwarp();
         }
+        if (lane == 0) r->objective = z;
     }
 }
 
