@@ -30,6 +30,26 @@ static uint64_t binom(int top, int k)
 
 #define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "FAILED %s:%d: %s  (n=%d m=%d)\n", __FILE__, __LINE__, #c, n, m); return 1; } } while (0)
 
+// make_weight_prefix: the table the device descent walks is the running sum of subtree_weight over the valid candidates
+static int check_prefix(int n, int m)
+{
+    auto C = [](int top, int k) -> uint64_t { return binom(top, k); };
+    const int P = m - kT;
+    const std::vector<uint64_t> ps = make_weight_prefix(C, n, m);
+    CHECK((int)ps.size() == P * (n + 1));
+    for (int i = 0; i < P; ++i) {
+        CHECK(ps[(size_t)i * (n + 1)] == 0);
+        for (int v = 0; v < n; ++v) {
+            const uint64_t want = v <= n - m + i ? subtree_weight(C, n, m, i, v) : 0;
+            CHECK(ps[(size_t)i * (n + 1) + v + 1] - ps[(size_t)i * (n + 1) + v] == want);
+        }
+    }
+    uint64_t total = 0;
+    for (int v = 0; v <= n - m; ++v) total += subtree_weight(C, n, m, 0, v);
+    CHECK(ps[n - m + 1] == total);
+    return 0;
+}
+
 static int run(int n, int m)
 {
     auto C = [](int top, int k) -> uint64_t { return binom(top, k); };
@@ -123,7 +143,7 @@ int main()
         if (run_handouts(h[0], h[1], h[2] - h[2] % kFineSplit, (uint32_t)h[3], h[4])) return 1;
     const int cases[][2] = {{6, 6}, {9, 6}, {12, 7}, {13, 8}, {16, 9}, {15, 10}, {18, 12}, {20, 16}, {24, 8}, {22, 9}};
     for (auto& c : cases)
-        if (run(c[0], c[1])) return 1;
+        if (run(c[0], c[1]) || check_prefix(c[0], c[1])) return 1;
     std::puts("test_weights: all passed");
     return 0;
 }
