@@ -48,6 +48,14 @@ def available() -> bool:
     return build() is not None
 
 
+def linear_algebra() -> str:
+    """'shim' (oracle/eigen_shim, the API stand-in) or 'eigen:<include dir>' — what the library was compiled against."""
+    try:
+        return open(os.path.join(_HERE, "_ref", "EIGEN")).read().strip() or "shim"
+    except OSError:
+        return "shim"
+
+
 def lib():
     global _LIB
     if _LIB is None:
