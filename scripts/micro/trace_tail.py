@@ -22,12 +22,16 @@ if len(sys.argv) > 5 and sys.argv[5] == "child":
     done = (C.c_ulonglong * 2)()
     L.enumgpu_trace_done(done)
     print("DONE", done[1])
+    ph = (C.c_ulonglong * (8 * 16 * 148))()
+    L.enumgpu_trace_phase(ph, len(ph))
+    tot = [sum(ph[8 * w + i] for w in range(16 * 148) if buf[4 * w + 1]) for i in range(8)]
+    print("PHASE", *tot)
     for w in range(16 * 148):
         if buf[4 * w + 1]:
             print("T", w // 16, w % 16, buf[4 * w], buf[4 * w + 1], buf[4 * w + 2], buf[4 * w + 3])
     sys.exit(0)
 out = subprocess.run([sys.executable, __file__] + sys.argv[1:5] + ["child"], capture_output=True, text=True).stdout
-rows, ms, done = [], None, 0
+rows, ms, done, phase = [], None, 0, None
 for line in out.splitlines():
     if line.startswith("LAUNCH"):
         rows = []
@@ -37,6 +41,8 @@ for line in out.splitlines():
         ms = float(line.split()[1])
     elif line.startswith("DONE"):
         done = int(line.split()[1])
+    elif line.startswith("PHASE"):
+        phase = [int(v) for v in line.split()[1:]]
 import numpy as np
 a = np.array(rows, dtype=np.int64)
 t0, t1, units, entry = a[:, 2], a[:, 3], a[:, 4], a[:, 5]
@@ -50,3 +56,9 @@ print(f"warps {len(a)}  kernel_ms(event) {ms:.3f}  span first-start..last-end {e
 print(f"start: max {start.max():.3f} ms   end: min {end.min():.3f} mean {end.mean():.3f} max {end.max():.3f}  -> idle tail mean {end.max() - end.mean():.3f} ms")
 print("end percentiles (ms):", " ".join(f"p{p}={np.percentile(end, p):.3f}" for p in (1, 10, 50, 90, 99)))
 print(f"units per warp: min {units.min()} mean {units.mean():.1f} max {units.max()}")
+if phase and sum(phase):
+    names = ["unit fetch + descent", "level q-1 from A", "levels q, q+1", "child / tail-group build", "leaves (setup + d loop + drains)", "end of parent (flush, successor)"]
+    tot = sum(phase)
+    n_units = int(units.sum())
+    print("warp cycles by phase: " + "; ".join(f"{nm} {100 * p / tot:.1f} %" for nm, p in zip(names, phase)))
+    print(f"per unit start ({n_units} units): fetch + descent {phase[0] / n_units / 1.965e3:.2f} us")
