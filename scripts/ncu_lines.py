@@ -61,7 +61,8 @@ for op, (c, s) in sorted(opagg.items(), key=lambda kv: -kv[1][0])[:28]:
 try:
     ksrc = open(os.path.join(root, "simplexmethod_b200", "csrc", "k_shared.cuh")).read().split("\n")
     marks = []
-    keys = (("__device__ __noinline__ void drain_fn", "drain_fn"), ("k_shared(const SharedParams sp", "prologue"),
+    keys = (("__device__ __noinline__ void drain2_fn", "drain2_fn"), ("__device__ __noinline__ void promote_fn", "promote_fn"),
+            ("k_shared(const SharedParams sp", "prologue"),
             ("------------- unit loop", "unit start (unrank, align)"), ("---- level QA from A", "level q-1 from A"),
             ("---- level Q (depth-q node)", "level q (one step)"), ("---- level Q+1 (parent)", "parent level"), ("---- children of this parent", "child level"),
             ("--------- leaves ---", "item setup (a,b,c)"), ("---- the shared loop over the last column", "d loop"),
