@@ -66,7 +66,7 @@ try:
             ("------------- unit loop", "unit start (unrank, align)"), ("---- level QA from A", "level q-1 from A"),
             ("---- level Q (depth-q node)", "level q (one step)"), ("---- level Q+1 (parent)", "parent level"), ("---- children of this parent", "child level"),
             ("--------- leaves ---", "item setup (a,b,c)"), ("---- the shared loop over the last column", "d loop"),
-            ("---- next child of the same parent", "next child / parent"), ("--------- reduction", "reduction"), ("// host side", "host"))
+            ("full groups of 32 go through", "batch end (promote calls)"), ("---- next child of the same parent", "next child / parent"), ("--------- reduction", "reduction"), ("// host side", "host"))
     for i, l in enumerate(ksrc, 1):
         for k, name in keys:
             if k in l:
