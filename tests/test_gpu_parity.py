@@ -299,6 +299,31 @@ def test_wide_and_tall_shapes_shared_kernel(gpu_lib, oracle, m, n, seed):
     assert_same(res, o, m)
 
 
+@pytest.mark.parametrize("m,n,seed,eps", [(8, 24, 1, 1e300), (10, 30, 1, 1e300), (7, 40, 2, 1e300), (12, 20, 3, 1e300),
+                                          (13, 19, 4, 1e300), (10, 30, 1, 5.0), (8, 24, 2, 3.0)])
+def test_survivor_stacks_under_pressure(gpu_lib, oracle, m, n, seed, eps):
+    """eps_feas so large that every basis (1e300) or a large share of them (5, 3) passes the five-component filter of
+    the leaves: every lane of every d-loop trip pushes an entry, a batch fills its first-stage stack to the bound it
+    was sized for (32 (n-4) on top of 31), and every basis goes through promote_fn and drain2_fn.  Counters, optimum
+    and tie-break must still be the oracle's."""
+    A, b, c, mx = lpgen.dense_lp(m, n, seed)
+    can = sm.Canonical(A, b, c, list(range(m)), minimize=not mx)
+    o, _ = oracle.solve(A, b, c, mx, n_threads=os.cpu_count(), eps_feas=eps)
+    if eps > 1e10:
+        assert o.n_infeasible == 0 and o.n_feasible + o.n_singular == o.n_bases
+    else:
+        assert o.n_feasible > o.n_bases // 10
+    for algo in ALGOS:
+        res = sm.EnumerationSolver(can, algo=algo, eps_feas=eps).enumerate()
+        assert res.algo_used == algo
+        assert_same(res, o, m)
+    for shards in (3,):
+        parts = [sm.EnumerationSolver(can, algo=_abi.ALGO_SHARED, eps_feas=eps).enumerate(shard_index=i, shard_count=shards)
+                 for i in range(shards)]
+        assert sum(p.n_feasible for p in parts) == o.n_feasible and sum(p.n_bases for p in parts) == o.n_bases
+        assert min((p.key, p.best_rank) for p in parts if p.status == 0) == (o.key, o.best_rank)
+
+
 def test_beyond_headline_size_properties(gpu_lib):
     """m=12, n=44 (21 090 682 613 bases, too many for the CPU oracle): size-independent properties —
     every rank falls in exactly one class, the optimum is HiGHS's, B x_B = b, and the result is the same for
