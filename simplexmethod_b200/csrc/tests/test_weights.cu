@@ -9,6 +9,8 @@
 //     with weight_of_child / weight_unrank;
 //   * handout_window: the hand-outs of all shards of a launch tile [w_lo, w_hi) exactly once, whole units first
 //     and the last round in kFineSplit pieces.
+//   * the closed form by which k_shared books the bases of a child's items [0, i) (restated here from the leaf code:
+//     the kernel's copy is a lambda over its shared-memory tables) against a walk over the item tables.
 // Exit code 0 = all passed.  Needs no GPU.
 #include <cstdio>
 #include <algorithm>
@@ -135,8 +137,44 @@ static int run_handouts(uint64_t w_lo, uint64_t span, uint64_t G, uint32_t shard
     return 0;
 }
 
+// Items are colex tuples; item i with largest element z carries R - 1 - z bases (R = candidates of the child, or
+// columns of the tail group).  k_shared: bases of the items before i = R C(z,t) - t C(z+1,t+1) + (i - C(z,t)) (R-1-z),
+// t = 3 for the triples of a child, 4 for the 4-tuples of a tail group (there with the tables sC3 / sC4 / C(.,5)).
+static int check_seen_closed_form()
+{
+    const int n = 0, m = 0;
+    for (int tail = 0; tail < 2; ++tail) {
+        const int r_lo = tail ? 5 : 4, r_hi = tail ? kTailR : 64;
+        for (int R = r_lo; R <= r_hi; ++R) {
+            const std::vector<uint32_t> items = tail ? make_quads(R - 1) : make_triples(R - 1);
+            CHECK(items.size() == binom(R - 1, tail ? 4 : 3));
+            uint64_t acc = 0;
+            for (size_t i = 0; i <= items.size(); ++i) {
+                uint64_t closed;
+                if (i == items.size()) closed = binom(R, tail ? 5 : 4);          // the kernel's `leaves`
+                else if (!tail) {
+                    const uint32_t z = (items[i] >> 16) & 255u;
+                    closed = (uint64_t)R * binom(z, 3) - 3u * binom(z + 1, 4) + (i - binom(z, 3)) * (uint64_t)(R - 1 - (int)z);
+                } else {
+                    const uint32_t z = items[i] >> 24;
+                    closed = (uint64_t)R * binom(z, 4) - 4u * binom(z + 1, 5) + (i - binom(z, 4)) * (uint64_t)(R - 1 - (int)z);
+                }
+                CHECK(closed == acc);
+                CHECK(closed < (1ull << 32));                                     // the kernel computes it in 32 bits
+                if (i < items.size()) {
+                    const uint32_t z = tail ? items[i] >> 24 : (items[i] >> 16) & 255u;
+                    CHECK((int)z <= R - 2);                                       // every item has at least one basis
+                    acc += (uint64_t)(R - 1 - (int)z);
+                }
+            }
+        }
+    }
+    return 0;
+}
+
 int main()
 {
+    if (check_seen_closed_form()) return 1;
     const uint64_t hcases[][5] = {{0, 1000000, 1024, 1, 16}, {77, 123457, 1024, 8, 4}, {5, 4096, 1024, 3, 64}, {0, 1023, 1024, 2, 8},
                                   {0, 5611770000ull, 21404, 8, 2368}, {1000, 5611770000ull, 21404, 1, 2368}, {0, 99999, 1028, 5, 7}};
     for (auto& h : hcases)
