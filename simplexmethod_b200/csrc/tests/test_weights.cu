@@ -10,7 +10,8 @@
 //   * handout_window: the hand-outs of all shards of a launch tile [w_lo, w_hi) exactly once, whole units first
 //     and the last round in kFineSplit pieces.
 //   * the closed form by which k_shared books the bases of a child's items [0, i) (restated here from the leaf code:
-//     the kernel's copy is a lambda over its shared-memory tables) against a walk over the item tables.
+//     the kernel's copy is a lambda over its shared-memory tables) against a walk over the item tables;
+//   * the sizes of the survivor stacks against the bound they must hold.
 // Exit code 0 = all passed.  Needs no GPU.
 #include <cstdio>
 #include <algorithm>
@@ -172,9 +173,24 @@ static int check_seen_closed_form()
     return 0;
 }
 
+// The first-stage survivor stack of a warp: at most 31 entries are left over when a batch of 32 items starts, and a lane
+// pushes at most one entry per column it owns — columns c+1 .. n-1 with c >= 4 (the prefix has at least two columns,
+// a < b < c above them).  16-byte stores need 16-byte aligned entries at every warp's offset.
+static int check_stack_sizes()
+{
+    const int m = 0;
+    for (int n = kSharedMinM; n <= kMaxN; ++n) {
+        CHECK(queue1_cap(n) >= 31 + 32 * (n - 5));
+        CHECK(queue_warp_bytes(n) % 16 == 0 && kQueue2Bytes % 16 == 0 && kQEntryBytes % 16 == 0);
+        CHECK(queue_warp_bytes(n) == (size_t)kQueue2Bytes + (size_t)queue1_cap(n) * kQEntryBytes);
+    }
+    static_assert(kQueue2Cap >= 31 + 32, "second stage: up to 31 waiting + 32 promoted at once");
+    return 0;
+}
+
 int main()
 {
-    if (check_seen_closed_form()) return 1;
+    if (check_seen_closed_form() || check_stack_sizes()) return 1;
     const uint64_t hcases[][5] = {{0, 1000000, 1024, 1, 16}, {77, 123457, 1024, 8, 4}, {5, 4096, 1024, 3, 64}, {0, 1023, 1024, 2, 8},
                                   {0, 5611770000ull, 21404, 8, 2368}, {1000, 5611770000ull, 21404, 1, 2368}, {0, 99999, 1028, 5, 7}};
     for (auto& h : hcases)
